@@ -1,0 +1,181 @@
+/*
+ * mmsbm_b200.h -- C ABI of libmmsbm_b200.so, the B200 (sm_100a) implementation
+ * of the EM hot path of eudald-seeslab/mmsbm.
+ *
+ * The reference has no FFI: its "operator API" for this path is the Python
+ * plugin contract of src/backend.py:16-22 (a module kernels_<name> exposing
+ * compute_omegas / update_coefficients / prod_dist) plus the driver contract of
+ * src/expectation_maximization.py:7-189 and the loop of src/mmsbm.py:187-269.
+ * Each entry point below names the reference interface it replaces.  The
+ * binding a maintainer of the reference would add (a ctypes stub) is shown in
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a positive cudaError_t value when the
+ *     CUDA runtime failed, or a negative MMSBM_E* code; no exception crosses the
+ *     ABI; mmsbm_last_error() returns a thread-local description;
+ *   - ``*_dev`` arguments are DEVICE pointers owned by the caller; ``stream`` is a
+ *     cudaStream_t passed as void*; device-level calls are asynchronous on that
+ *     stream, allocate nothing and keep no global state (re-entrant across
+ *     streams and devices).  Workspace is caller-provided; ask *_workspace_bytes;
+ *   - ``mmsbm_host_*`` functions take HOST pointers, allocate and free their own
+ *     device memory on the current device, and return after synchronising;
+ *   - ids are int32 on the device (N <= 2^31-1), int64 [N,3] row-major at the
+ *     host surface exactly as the reference's encoded ``data`` array;
+ *   - parameters are float64.  Device layout for S runs (``sampling``):
+ *         theta [S][U][ldk]   eta [S][I][ldl]   pr [S][K][L][R]
+ *     with ldk = K rounded up to even, ldl likewise (rows are 16-byte multiples
+ *     for 128-bit loads); padding columns must be zero.  Host layout is the
+ *     reference's: theta [S][U][K], eta [S][I][L], pr [S][K][L][R], C order.
+ *
+ * Index structure ("graph"): rows grouped by (user, rating) and by
+ * (item, rating), original row order kept inside a group:
+ *         useg [U*R+1]  start of group (u,r) in uadj/uperm
+ *         uadj [N]      item id of each row, in (u, r, row) order
+ *         uperm[N]      original row index (== stable argsort of u*R+r)
+ *         udeg [U]      number of rows of user u
+ *   and iseg/iadj/iperm/ideg symmetrically (iadj holds user ids).
+ * This holds what the reference keeps as per-id row lists
+ * (src/mmsbm.py:100-122): group (a,r) = _user_indices[a] & _rating_indices[r].
+ */
+#ifndef MMSBM_B200_H
+#define MMSBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMSBM_ABI_VERSION 1
+
+#define MMSBM_EINVAL  (-1)   /* bad argument (null pointer, size out of range)      */
+#define MMSBM_ERANGE  (-2)   /* shape not supported (K or L > 256, id*R overflows)   */
+#define MMSBM_ENOMEM  (-3)   /* workspace too small                                  */
+#define MMSBM_ENODEV  (-4)   /* no usable CUDA device (there is no CPU fallback)     */
+
+/* flags of mmsbm_em_step / mmsbm_em_run */
+#define MMSBM_RAW_THETA   1  /* theta_out = unnormalised n_theta (src/kernels_numpy.py:63-65)   */
+#define MMSBM_RAW_ETA_PR  2  /* eta_out, pr_out = unnormalised n_eta, n_pr; the caller
+                                all-reduces them over ranks, then calls mmsbm_em_finalize */
+
+int         mmsbm_abi_version(void);
+const char* mmsbm_last_error(void);
+/* number of CUDA devices visible, or a negative code; never falls back to CPU */
+int         mmsbm_device_count(void);
+/* kernels launched by this library on the calling thread since it was loaded */
+int64_t     mmsbm_launch_count(void);
+
+/* ---- a8: index structure, replaces MMSBM._prepare_objects (src/mmsbm.py:93-122) -------- */
+int mmsbm_graph_workspace_bytes(int64_t n_ratings, int32_t n_users, int32_t n_items,
+                                int32_t n_levels, size_t* bytes);
+int mmsbm_graph_build(const int32_t* user_dev, const int32_t* item_dev, const int32_t* level_dev,
+                      int64_t n_ratings, int32_t n_users, int32_t n_items, int32_t n_levels,
+                      int32_t* useg_dev, int32_t* uadj_dev, int32_t* uperm_dev, int32_t* udeg_dev,
+                      int32_t* iseg_dev, int32_t* iadj_dev, int32_t* iperm_dev, int32_t* ideg_dev,
+                      void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- a2+a3+a4: one EM iteration for S runs, replaces update_coefficients
+ *      (src/kernels_numpy.py:43-79) + normalize_with_d x2 + normalize_with_self
+ *      (src/expectation_maximization.py:118-155), i.e. the loop body src/mmsbm.py:244-250 --- */
+int mmsbm_em_workspace_bytes(int32_t n_users, int32_t n_items, int32_t n_levels,
+                             int32_t K, int32_t L, int32_t n_runs, size_t* bytes);
+int mmsbm_em_step(const int32_t* useg_dev, const int32_t* uadj_dev, const int32_t* udeg_dev,
+                  const int32_t* iseg_dev, const int32_t* iadj_dev, const int32_t* ideg_dev,
+                  int64_t n_ratings, int32_t n_users, int32_t n_items, int32_t n_levels,
+                  int32_t K, int32_t L, int32_t n_runs,
+                  const double* theta_dev, const double* eta_dev, const double* pr_dev,
+                  double* theta_out_dev, double* eta_out_dev, double* pr_out_dev,
+                  int32_t flags, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* the same step with CUDA events around its four launches (measurement only: it waits for
+ * the stream); ms4 = device ms of {by-user pass, by-item pass, pr accumulate, pr finalize} */
+int mmsbm_em_step_profiled(const int32_t* useg_dev, const int32_t* uadj_dev, const int32_t* udeg_dev,
+                           const int32_t* iseg_dev, const int32_t* iadj_dev, const int32_t* ideg_dev,
+                           int64_t n_ratings, int32_t n_users, int32_t n_items, int32_t n_levels,
+                           int32_t K, int32_t L, int32_t n_runs,
+                           const double* theta_dev, const double* eta_dev, const double* pr_dev,
+                           double* theta_out_dev, double* eta_out_dev, double* pr_out_dev,
+                           int32_t flags, void* workspace_dev, size_t workspace_bytes, void* stream,
+                           float* ms4);
+/* ``iterations`` steps ping-ponging between (theta,eta,pr)_a and _b, no host sync;
+ * the result is in the _a buffers when iterations is even, else in _b.
+ * Replaces the loop src/mmsbm.py:243-250. */
+int mmsbm_em_run(const int32_t* useg_dev, const int32_t* uadj_dev, const int32_t* udeg_dev,
+                 const int32_t* iseg_dev, const int32_t* iadj_dev, const int32_t* ideg_dev,
+                 int64_t n_ratings, int32_t n_users, int32_t n_items, int32_t n_levels,
+                 int32_t K, int32_t L, int32_t n_runs, int32_t iterations,
+                 double* theta_a_dev, double* eta_a_dev, double* pr_a_dev,
+                 double* theta_b_dev, double* eta_b_dev, double* pr_b_dev,
+                 void* workspace_dev, size_t workspace_bytes, void* stream);
+/* post-all-reduce epilogue of a rating-sharded run: eta = n_eta / max(deg,1),
+ * pr normalised over the rating axis (zero sums divide by one). In place. */
+int mmsbm_em_finalize(double* eta_dev, const int32_t* ideg_dev, int32_t n_items, int32_t L,
+                      double* pr_dev, int32_t K, int32_t n_levels, int32_t n_runs, void* stream);
+
+/* ---- a5: the reference's "likelihood", replaces ExpectationMaximization.compute_likelihood
+ *      (src/expectation_maximization.py:157-167); out_dev[S] ------------------------------ */
+int mmsbm_likelihood_workspace_bytes(int32_t n_users, int32_t n_runs, size_t* bytes);
+int mmsbm_likelihood(const int32_t* useg_dev, const int32_t* uadj_dev,
+                     int64_t n_ratings, int32_t n_users, int32_t n_items, int32_t n_levels,
+                     int32_t K, int32_t L, int32_t n_runs,
+                     const double* theta_dev, const double* eta_dev, const double* pr_dev,
+                     double* out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- a6: rat[s][m][r], replaces prod_dist (src/kernels_numpy.py:86-97) ------------------ */
+int mmsbm_prod_dist(const int32_t* user_dev, const int32_t* item_dev, int64_t n_rows,
+                    int32_t n_users, int32_t n_items, int32_t n_levels,
+                    int32_t K, int32_t L, int32_t n_runs,
+                    const double* theta_dev, const double* eta_dev, const double* pr_dev,
+                    double* rat_dev, void* stream);
+
+/* ---- a10: prediction statistics, replaces MMSBM._compute_indicators/_compute_final_stats
+ *      (src/mmsbm.py:488-539).  counts_dev [S][5] int64 = {rows kept, exact, one-off,
+ *      sum |pred-real|, real == rint(E[r])}; s2pond_dev [S] double.  pred_dev [S][M] int32
+ *      (argmax, first maximum) may be null.  mean over runs: src/mmsbm.py:315 ------------ */
+int mmsbm_stats_workspace_bytes(int64_t n_rows, int32_t n_runs, size_t* bytes);
+int mmsbm_predict_stats(const double* rat_dev, const int32_t* real_dev, int64_t n_rows,
+                        int32_t n_levels, int32_t n_runs, int64_t* counts_dev, double* s2pond_dev,
+                        int32_t* pred_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+int mmsbm_mean_over_runs(const double* rat_dev, int64_t n_elems, int32_t n_runs,
+                         double* mean_dev, void* stream);
+
+/* ---- a1: materialised omega[N][K][L] for ONE run (plugin shim only; small N),
+ *      replaces compute_omegas (src/kernels_numpy.py:21-36) ------------------------------ */
+int mmsbm_compute_omegas(const int32_t* user_dev, const int32_t* item_dev, const int32_t* level_dev,
+                         int64_t n_ratings, int32_t K, int32_t L, int32_t n_levels,
+                         const double* theta_dev, const double* eta_dev, const double* pr_dev,
+                         double* omegas_dev, void* stream);
+
+/* ================= host-pointer entry points (what the ctypes stub binds) ================= */
+/* plugin b1 (src/backend.py:22): numpy in, numpy out, data int64 [N,3] */
+int mmsbm_host_compute_omegas(const int64_t* data, int64_t n_ratings,
+                              const double* theta, int32_t n_users, int32_t K,
+                              const double* eta, int32_t n_items, int32_t L,
+                              const double* pr, int32_t n_levels, double* omegas_out);
+int mmsbm_host_update_coefficients(const int64_t* data, int64_t n_ratings,
+                                   const double* theta, int32_t n_users, int32_t K,
+                                   const double* eta, int32_t n_items, int32_t L,
+                                   const double* pr, int32_t n_levels,
+                                   double* n_theta_out, double* n_eta_out, double* n_pr_out);
+int mmsbm_host_prod_dist(const int64_t* data, int64_t n_rows,
+                         const double* theta, int32_t n_users, int32_t K,
+                         const double* eta, int32_t n_items, int32_t L,
+                         const double* pr, int32_t n_levels, double* rat_out);
+int mmsbm_host_likelihood(const int64_t* data, int64_t n_ratings,
+                          const double* theta, int32_t n_users, int32_t K,
+                          const double* eta, int32_t n_items, int32_t L,
+                          const double* pr, int32_t n_levels, double* out);
+/* S whole runs of src/mmsbm.py:187-269 from caller-supplied theta0/eta0/pr0 (the seeded
+ * host draws of :224-233): index build, ``iterations`` EM steps, final likelihood.
+ * Outputs in the host layout; likelihood_out[S]. */
+int mmsbm_host_fit(const int64_t* data, int64_t n_ratings,
+                   int32_t n_users, int32_t n_items, int32_t n_levels,
+                   int32_t K, int32_t L, int32_t n_runs, int32_t iterations,
+                   const double* theta0, const double* eta0, const double* pr0,
+                   double* theta_out, double* eta_out, double* pr_out, double* likelihood_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMSBM_B200_H */

@@ -1,0 +1,335 @@
+// On-device reductions around the EM loop: the reference's "likelihood"
+// (src/expectation_maximization.py:157-167), prod_dist (src/kernels_numpy.py:86-97), the
+// prediction statistics (src/mmsbm.py:488-539), the mean over runs (src/mmsbm.py:315) and a
+// materialising compute_omegas (src/kernels_numpy.py:21-36) for the plugin shim.
+// All sums are two-stage with a fixed order (bit-reproducible).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace mmsbm {
+
+constexpr int kLikWarps = 8;
+constexpr int kLikCtas = 148 * 4;   // persistent CTAs per run
+
+// ---- likelihood ----------------------------------------------------------------------------
+// sum_n sum_kl w~ (log w~ - log S~_n), w~ = max(theta_k eta_l pr_klr, eps), S~ = max(sum w, eps).
+// Not factorisable (the clamp and the log act on each (k,l)), so every rating costs K*L logs.
+// One warp walks whole user segments of the (user, rating)-grouped index: theta_u is staged
+// once per user, the rating level is implied by the group; lanes own l, the loop runs over k.
+struct LikArgs {
+  const int32_t* useg; const int32_t* uadj;
+  const double* theta; const double* eta; const double* pr;
+  double* partial;      // [S][kLikCtas*kLikWarps]
+  int U, I, R, K, L, ldk, ldl;
+};
+
+__global__ void __launch_bounds__(kLikWarps * 32) likelihood_kernel(const LikArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int K = A.K, L = A.L, R = A.R;
+  double* Pq = reinterpret_cast<double*>(smem_raw);          // [R][K][L]
+  double* th_s = Pq + (size_t)R * K * L;                     // [warps][K]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int run = blockIdx.y;
+  const double* prs = A.pr + (size_t)run * K * L * R;
+  for (int t = threadIdx.x; t < K * L * R; t += blockDim.x) {
+    int kl = t / R, r = t - kl * R;
+    Pq[(size_t)r * K * L + kl] = __ldg(prs + t);
+  }
+  __syncthreads();
+  double* th = th_s + warp * K;
+  const double* theta_run = A.theta + (size_t)run * A.U * A.ldk;
+  const double* eta_run = A.eta + (size_t)run * A.I * A.ldl;
+  const int gw = blockIdx.x * kLikWarps + warp, nw = gridDim.x * kLikWarps;
+  double acc = 0.0;
+  for (int u = gw; u < A.U; u += nw) {
+    __syncwarp();
+    for (int k = lane; k < K; k += 32) th[k] = __ldg(theta_run + (size_t)u * A.ldk + k);
+    __syncwarp();
+    for (int r = 0; r < R; ++r) {
+      const int lo = __ldg(A.useg + (size_t)u * R + r), hi = __ldg(A.useg + (size_t)u * R + r + 1);
+      const double* Pr = Pq + (size_t)r * K * L;
+      for (int j = lo; j < hi; ++j) {
+        const int item = __ldg(A.uadj + j);
+        const double* erow = eta_run + (size_t)item * A.ldl;
+        double tot = 0.0;
+        for (int l0 = 0; l0 < L; l0 += 32) {
+          const int l = l0 + lane;
+          if (l < L) {
+            const double e = __ldg(erow + l);
+            for (int k = 0; k < K; ++k) tot += __dmul_rn(__dmul_rn(th[k], e), Pr[k * L + l]);
+          }
+        }
+        tot = warp_sum(tot);
+        const double ls = log(fmax(tot, kEps));
+        for (int l0 = 0; l0 < L; l0 += 32) {
+          const int l = l0 + lane;
+          if (l < L) {
+            const double e = __ldg(erow + l);
+            for (int k = 0; k < K; ++k) {
+              const double w = fmax(__dmul_rn(__dmul_rn(th[k], e), Pr[k * L + l]), kEps);
+              acc += __dsub_rn(__dmul_rn(w, log(w)), __dmul_rn(w, ls));
+            }
+          }
+        }
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) A.partial[(size_t)run * nw + gw] = acc;
+}
+
+__global__ void __launch_bounds__(256) sum_partials_kernel(const double* partial, int n, double* out) {
+  __shared__ double sm[256];
+  const double* p = partial + (size_t)blockIdx.x * n;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += p[i];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sm[0];
+}
+
+// ---- prod_dist -----------------------------------------------------------------------------
+struct ProdArgs {
+  const int32_t* user; const int32_t* item;
+  const double* theta; const double* eta; const double* pr;
+  double* rat;          // [S][M][R]
+  int64_t M;
+  int U, I, R, K, L, ldk, ldl;
+};
+
+__global__ void __launch_bounds__(256) prod_dist_kernel(const ProdArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int K = A.K, L = A.L, R = A.R;
+  double* Pq = reinterpret_cast<double*>(smem_raw);          // [R][K][L]
+  double* th_s = Pq + (size_t)R * K * L;                     // [warps][K]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int run = blockIdx.y;
+  const double* prs = A.pr + (size_t)run * K * L * R;
+  for (int t = threadIdx.x; t < K * L * R; t += blockDim.x) {
+    int kl = t / R, r = t - kl * R;
+    Pq[(size_t)r * K * L + kl] = __ldg(prs + t);
+  }
+  __syncthreads();
+  double* th = th_s + warp * K;
+  const double* theta_run = A.theta + (size_t)run * A.U * A.ldk;
+  const double* eta_run = A.eta + (size_t)run * A.I * A.ldl;
+  for (int64_t m = (int64_t)blockIdx.x * nwarp + warp; m < A.M; m += (int64_t)gridDim.x * nwarp) {
+    const int u = __ldg(A.user + m), it = __ldg(A.item + m);
+    __syncwarp();
+    for (int k = lane; k < K; k += 32) th[k] = __ldg(theta_run + (size_t)u * A.ldk + k);
+    __syncwarp();
+    const double* erow = eta_run + (size_t)it * A.ldl;
+    for (int r = 0; r < R; ++r) {
+      const double* Pr = Pq + (size_t)r * K * L;
+      double acc = 0.0;
+      for (int l0 = 0; l0 < L; l0 += 32) {
+        const int l = l0 + lane;
+        if (l < L) {
+          const double e = __ldg(erow + l);
+          for (int k = 0; k < K; ++k) acc = fma(th[k] * e, Pr[k * L + l], acc);
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) A.rat[((size_t)run * A.M + m) * R + r] = acc;
+    }
+  }
+}
+
+// ---- prediction statistics -----------------------------------------------------------------
+struct StatArgs {
+  const double* rat; const int32_t* real;
+  int64_t M; int R;
+  int64_t* cnt_partial;   // [S][blocks][5]
+  double* s2_partial;     // [S][blocks]
+  int32_t* pred;          // [S][M] or null
+};
+
+__global__ void __launch_bounds__(256) stats_kernel(const StatArgs A) {
+  __shared__ long long c_s[256][5];
+  __shared__ double d_s[256];
+  const int run = blockIdx.y;
+  long long c[5] = {0, 0, 0, 0, 0};
+  double s2p = 0.0;
+  for (int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x; m < A.M; m += (int64_t)gridDim.x * 256) {
+    const double* row = A.rat + ((size_t)run * A.M + m) * A.R;
+    double best = row[0], tot = 0.0, expect = 0.0;
+    int arg = 0;
+    for (int r = 0; r < A.R; ++r) {
+      const double v = row[r];
+      if (v > best) { best = v; arg = r; }   // first maximum, as np.argmax
+      tot += v;
+      expect = fma(v, (double)r, expect);    // rat @ [0..R-1]  (src/mmsbm.py:518)
+    }
+    if (A.pred) A.pred[(size_t)run * A.M + m] = arg;
+    if (tot != 0.0) {                        // rows with an all-zero distribution are dropped
+      const int real = A.real[m];
+      const int gap = abs(arg - real);
+      c[0] += 1;
+      c[1] += (gap == 0);
+      c[2] += (gap <= 1);
+      c[3] += gap;
+      c[4] += ((double)real == rint(expect));  // np.round: half to even
+      s2p += fabs(expect - (double)real);
+    }
+  }
+  for (int k = 0; k < 5; ++k) c_s[threadIdx.x][k] = c[k];
+  d_s[threadIdx.x] = s2p;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      for (int k = 0; k < 5; ++k) c_s[threadIdx.x][k] += c_s[threadIdx.x + s][k];
+      d_s[threadIdx.x] += d_s[threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const size_t b = (size_t)run * gridDim.x + blockIdx.x;
+    for (int k = 0; k < 5; ++k) A.cnt_partial[b * 5 + k] = c_s[0][k];
+    A.s2_partial[b] = d_s[0];
+  }
+}
+
+__global__ void stats_final_kernel(const int64_t* cnt_partial, const double* s2_partial, int blocks,
+                                   int64_t* counts, double* s2pond) {
+  const int run = blockIdx.x;
+  if (threadIdx.x < 5) {
+    long long acc = 0;
+    for (int b = 0; b < blocks; ++b) acc += cnt_partial[((size_t)run * blocks + b) * 5 + threadIdx.x];
+    counts[run * 5 + threadIdx.x] = acc;
+  } else if (threadIdx.x == 5) {
+    double acc = 0.0;
+    for (int b = 0; b < blocks; ++b) acc += s2_partial[(size_t)run * blocks + b];
+    s2pond[run] = acc;
+  }
+}
+
+__global__ void mean_runs_kernel(const double* rat, int64_t n, int S, double* mean) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double acc = rat[t];
+  for (int s = 1; s < S; ++s) acc += rat[(size_t)s * n + t];   // slab order, as np.mean(axis=0)
+  mean[t] = acc / (double)S;
+}
+
+__global__ void omegas_kernel(const int32_t* user, const int32_t* item, const int32_t* level,
+                              int64_t total, int K, int L, int R, int ldk, int ldl,
+                              const double* theta, const double* eta, const double* pr, double* out) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int KL = K * L;
+  const int64_t n = t / KL;
+  const int kl = (int)(t - n * KL), k = kl / L, l = kl - k * L;
+  const int u = user[n], i = item[n], r = level[n];
+  // (theta * eta) * pr, the reference's left-to-right product (src/kernels_numpy.py:32-36)
+  out[t] = __dmul_rn(__dmul_rn(theta[(size_t)u * ldk + k], eta[(size_t)i * ldl + l]),
+                     pr[(size_t)kl * R + r]);
+}
+
+constexpr int kStatBlocks = 296;
+
+}  // namespace mmsbm
+
+using namespace mmsbm;
+
+extern "C" int mmsbm_likelihood_workspace_bytes(int32_t U, int32_t S, size_t* bytes) {
+  MMSBM_REQUIRE(bytes && U > 0 && S > 0, MMSBM_EINVAL, "mmsbm_likelihood_workspace_bytes: bad argument");
+  *bytes = align_up((size_t)S * kLikCtas * kLikWarps * 8) + 256;
+  return 0;
+}
+
+extern "C" int mmsbm_likelihood(const int32_t* useg, const int32_t* uadj, int64_t N, int32_t U,
+                                int32_t I, int32_t R, int32_t K, int32_t L, int32_t S,
+                                const double* theta, const double* eta, const double* pr, double* out,
+                                void* ws, size_t ws_bytes, void* stream) {
+  MMSBM_REQUIRE(useg && uadj && theta && eta && pr && out && ws, MMSBM_EINVAL,
+                "mmsbm_likelihood: null pointer");
+  MMSBM_REQUIRE(U > 0 && I > 0 && R > 0 && K > 0 && L > 0 && S > 0 && N >= 0, MMSBM_EINVAL,
+                "mmsbm_likelihood: bad size");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena arena(ws, ws_bytes);
+  const int nw = kLikCtas * kLikWarps;
+  double* partial = arena.take<double>((size_t)S * nw);
+  MMSBM_REQUIRE(partial, MMSBM_ENOMEM, "mmsbm_likelihood: workspace too small");
+  LikArgs a{useg, uadj, theta, eta, pr, partial, U, I, R, K, L, round_even(K), round_even(L)};
+  size_t smem = ((size_t)R * K * L + (size_t)kLikWarps * K) * 8;
+  MMSBM_REQUIRE(smem <= 227 * 1024, MMSBM_ERANGE, "mmsbm_likelihood: K*L*R too large for shared memory");
+  MMSBM_CUDA(cudaFuncSetAttribute(likelihood_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  likelihood_kernel<<<dim3(kLikCtas, S), kLikWarps * 32, smem, st>>>(a);
+  MMSBM_LAUNCH_CHECK("likelihood_kernel");
+  sum_partials_kernel<<<S, 256, 0, st>>>(partial, nw, out);
+  MMSBM_LAUNCH_CHECK("sum_partials_kernel");
+  return 0;
+}
+
+extern "C" int mmsbm_prod_dist(const int32_t* user, const int32_t* item, int64_t M, int32_t U,
+                               int32_t I, int32_t R, int32_t K, int32_t L, int32_t S,
+                               const double* theta, const double* eta, const double* pr, double* rat,
+                               void* stream) {
+  MMSBM_REQUIRE(theta && eta && pr && (M == 0 || (user && item && rat)), MMSBM_EINVAL,
+                "mmsbm_prod_dist: null pointer");
+  MMSBM_REQUIRE(U > 0 && I > 0 && R > 0 && K > 0 && L > 0 && S > 0 && M >= 0, MMSBM_EINVAL,
+                "mmsbm_prod_dist: bad size");
+  if (M == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProdArgs a{user, item, theta, eta, pr, rat, M, U, I, R, K, L, round_even(K), round_even(L)};
+  size_t smem = ((size_t)R * K * L + 8 * (size_t)K) * 8;
+  MMSBM_REQUIRE(smem <= 227 * 1024, MMSBM_ERANGE, "mmsbm_prod_dist: K*L*R too large for shared memory");
+  MMSBM_CUDA(cudaFuncSetAttribute(prod_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t want = (M + 7) / 8;
+  unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+  prod_dist_kernel<<<dim3(grid, S), 256, smem, st>>>(a);
+  MMSBM_LAUNCH_CHECK("prod_dist_kernel");
+  return 0;
+}
+
+extern "C" int mmsbm_stats_workspace_bytes(int64_t M, int32_t S, size_t* bytes) {
+  MMSBM_REQUIRE(bytes && M >= 0 && S > 0, MMSBM_EINVAL, "mmsbm_stats_workspace_bytes: bad argument");
+  *bytes = align_up((size_t)S * kStatBlocks * 5 * 8) + align_up((size_t)S * kStatBlocks * 8) + 256;
+  return 0;
+}
+
+extern "C" int mmsbm_predict_stats(const double* rat, const int32_t* real, int64_t M, int32_t R,
+                                   int32_t S, int64_t* counts, double* s2pond, int32_t* pred, void* ws,
+                                   size_t ws_bytes, void* stream) {
+  MMSBM_REQUIRE(counts && s2pond && ws && (M == 0 || (rat && real)), MMSBM_EINVAL,
+                "mmsbm_predict_stats: null pointer");
+  MMSBM_REQUIRE(M >= 0 && R > 0 && S > 0, MMSBM_EINVAL, "mmsbm_predict_stats: bad size");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena arena(ws, ws_bytes);
+  int64_t* cp = arena.take<int64_t>((size_t)S * kStatBlocks * 5);
+  double* sp = arena.take<double>((size_t)S * kStatBlocks);
+  MMSBM_REQUIRE(cp && sp, MMSBM_ENOMEM, "mmsbm_predict_stats: workspace too small");
+  StatArgs a{rat, real, M, R, cp, sp, pred};
+  stats_kernel<<<dim3(kStatBlocks, S), 256, 0, st>>>(a);
+  MMSBM_LAUNCH_CHECK("stats_kernel");
+  stats_final_kernel<<<S, 32, 0, st>>>(cp, sp, kStatBlocks, counts, s2pond);
+  MMSBM_LAUNCH_CHECK("stats_final_kernel");
+  return 0;
+}
+
+extern "C" int mmsbm_mean_over_runs(const double* rat, int64_t n, int32_t S, double* mean, void* stream) {
+  MMSBM_REQUIRE((n == 0 || (rat && mean)) && n >= 0 && S > 0, MMSBM_EINVAL, "mmsbm_mean_over_runs: bad argument");
+  if (n == 0) return 0;
+  mean_runs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rat, n, S, mean);
+  MMSBM_LAUNCH_CHECK("mean_runs_kernel");
+  return 0;
+}
+
+extern "C" int mmsbm_compute_omegas(const int32_t* user, const int32_t* item, const int32_t* level,
+                                    int64_t N, int32_t K, int32_t L, int32_t R, const double* theta,
+                                    const double* eta, const double* pr, double* omegas, void* stream) {
+  MMSBM_REQUIRE(theta && eta && pr && (N == 0 || (user && item && level && omegas)), MMSBM_EINVAL,
+                "mmsbm_compute_omegas: null pointer");
+  MMSBM_REQUIRE(N >= 0 && K > 0 && L > 0 && R > 0, MMSBM_EINVAL, "mmsbm_compute_omegas: bad size");
+  if (N == 0) return 0;
+  const int64_t total = N * K * L;
+  omegas_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      user, item, level, total, K, L, R, round_even(K), round_even(L), theta, eta, pr, omegas);
+  MMSBM_LAUNCH_CHECK("omegas_kernel");
+  return 0;
+}

@@ -1,0 +1,137 @@
+"""String-rank encoding of (user, item, rating) columns.
+
+Same observable behaviour as the reference's DataHandler (src/data_handler.py:10-144):
+every cell is ``str()``-ed, ids are ranked by ``sorted(set(strings))`` (lexicographic:
+'10' < '2'), train rows are encoded to an int64 ``[N,3]`` array, test rows whose
+user / item / rating was not seen in training are dropped with a warning, and fitted
+parameters are decoded back to the original labels.  The python-level ``str`` runs
+once per DISTINCT value, not once per cell; the result is identical.
+"""
+import logging
+
+import numpy as np
+import pandas as pd
+
+from .helpers import _invert_dict
+
+
+def _stringify(col):
+    """Per-cell ``str(x)`` of a pandas column as an object ndarray
+    (src/data_handler.py:27-32, via ``.tolist()`` so numpy scalars print as python ones)."""
+    values = col.tolist()
+    kind = col.dtype.kind if hasattr(col.dtype, "kind") else "O"
+    if kind in "iub" and len(values) > 64:
+        arr = col.to_numpy()
+        uniq, inv = np.unique(arr, return_inverse=True)
+        table = np.array([str(v) for v in uniq.tolist()], dtype=object)
+        return table[inv]
+    return np.array([str(x) for x in values], dtype=object)
+
+
+def _rank_table(strings):
+    """{string: rank in sorted(set(strings))} (src/data_handler.py:39-44)."""
+    return {s: k for k, s in enumerate(sorted(set(strings.tolist())))}
+
+
+def _encode(strings, table):
+    uniq, inv = np.unique(strings.astype(str), return_inverse=True) if len(strings) > 64 \
+        else (None, None)
+    if uniq is None:
+        return np.array([table[s] for s in strings.tolist()], dtype=np.int64)
+    codes = np.array([table[s] for s in uniq.tolist()], dtype=np.int64)
+    return codes[inv]
+
+
+class DataHandler:
+    obs_dict = None
+    items_dict = None
+    ratings_dict = None
+
+    def __init__(self):
+        pass
+
+    @staticmethod
+    def _get_data(path_):
+        return pd.read_csv(path_, sep=None, usecols=[0, 1, 2], engine="python")
+
+    @staticmethod
+    def _check_data(df):
+        assert df.isnull().sum().sum() == 0, "Data contains missing values. Aborting."
+
+    @staticmethod
+    def _to_object_str(data):
+        out = data.copy()
+        for col in out.columns:
+            out[col] = pd.Series(_stringify(out[col]), index=out.index, dtype=object)
+        return out
+
+    @staticmethod
+    def _create_values_dict(x):
+        return _rank_table(np.asarray([str(a) for a in x], dtype=object))
+
+    @staticmethod
+    def _rename_values(x, dict_):
+        return [dict_[str(a)] for a in x]
+
+    def parse_train_data(self, df):
+        cols = [df.iloc[:, c].to_numpy(dtype=object) for c in range(3)]
+        self.obs_dict, self.items_dict, self.ratings_dict = (_rank_table(c) for c in cols)
+        out = np.empty((len(df), 3), dtype=np.int64)
+        for c, table in enumerate((self.obs_dict, self.items_dict, self.ratings_dict)):
+            out[:, c] = _encode(cols[c], table)
+        return out
+
+    def parse_test_data(self, df):
+        out = np.empty((len(df), 3), dtype=np.int64)
+        for c, table in enumerate((self.obs_dict, self.items_dict, self.ratings_dict)):
+            out[:, c] = _encode(df.iloc[:, c].to_numpy(dtype=object), table)
+        return out
+
+    @staticmethod
+    def return_original_indices(x, dict_):
+        inv = _invert_dict(dict_)
+        return [inv[a] for a in x]
+
+    def return_theta_indices(self, theta):
+        theta = pd.DataFrame(theta)
+        theta.index = self.return_original_indices(theta.index, self.obs_dict)
+        return theta
+
+    def return_eta_indices(self, eta):
+        eta = pd.DataFrame(eta)
+        eta.index = self.return_original_indices(eta.index, self.items_dict)
+        return eta
+
+    def return_pr_indices(self, pr):
+        inv = _invert_dict(self.ratings_dict)
+        return {inv[a]: pd.DataFrame(pr[:, :, a]) for a in range(pr.shape[2])}
+
+    def format_train_data(self, data):
+        data = self._to_object_str(data)
+        self._check_data(data)
+        return self.parse_train_data(data)
+
+    def _check_test_in_train(self, data):
+        """Column by column (users, items, ratings -- looked up BY NAME like the
+        reference, src/data_handler.py:112-127): warn about the unseen values among the
+        rows still present and drop those rows."""
+        logger = logging.getLogger("MMSBM")
+        for column, table in (("users", self.obs_dict), ("items", self.items_dict),
+                              ("ratings", self.ratings_dict)):
+            present = set(str(a) for a in data.loc[:, column])
+            unseen = present.difference(table.keys())
+            if len(unseen):
+                logger.warning(
+                    f"The {column} {', '.join(str(a) for a in unseen)} are in the test set but weren't in "
+                    f"the train set so I'll remove them.")
+                data = data[~data.loc[:, column].isin(unseen)]
+        return data
+
+    def format_test_data(self, data):
+        data = self._to_object_str(data)
+        self._check_data(data)
+        data = self._check_test_in_train(data)
+        return self.parse_test_data(data)
+
+    def return_dicts(self):
+        return self.obs_dict, self.items_dict, self.ratings_dict

@@ -1,0 +1,289 @@
+"""Mixed-Membership Stochastic Block Model with the public API of the reference
+(src/mmsbm.py:15-553): ``MMSBM(user_groups, item_groups, iterations, sampling, seed,
+debug, backend).fit / cv_fit / predict / score``.
+
+What differs is where the work runs.  The reference fans ``sampling`` runs out to a
+spawn pool and loops ``update_coefficients`` + three normalisations in numpy
+(src/mmsbm.py:182-185, 243-250); here all runs of a rank are batched on one B200:
+the index structure, the fused EM iterations, the likelihood, prod_dist and the
+prediction statistics are CUDA kernels of libmmsbm_b200.so (engine.py), and runs
+shard over GPUs when torch.distributed is initialised (parallel.py).  Kept on the
+host, verbatim in behaviour: the string-rank encoding, the seeded initial draws
+(numpy PCG64 streams of the SeedSequence children, src/mmsbm.py:82-85,224-233 -- so run
+s starts from the same theta0/eta0/pr0 as in the reference) and the fold construction
+of cv_fit (it consumes ``self.rng`` sequentially).
+"""
+from datetime import datetime
+
+import numpy as np
+
+from .data_handler import DataHandler
+from .engine import Engine, predict_stats
+from .expectation_maximization import ExpectationMaximization
+from .helpers import get_n_per_group, structure_folds
+from .logger import setup_logger
+from .parallel import dist_info, gather_runs, shard_runs
+
+
+class MMSBM:
+    """
+    Parameters
+    ----------
+    user_groups, item_groups : int
+        Number of latent user / item groups (K, L).
+    iterations : int, default=400
+        EM iterations per run.
+    sampling : int, default=1
+        Independent randomly initialised runs; all are kept, the best one (by accuracy
+        on the data given to ``predict``, src/mmsbm.py:306,474-478) provides theta/eta/pr.
+    seed : int or None
+        Seed of the parent generator; run s uses the s-th SeedSequence child.
+    debug : bool
+        Log the likelihood every 50 iterations.
+    backend : str, default="auto"
+        "auto" or "b200".  There is no CPU backend.
+    """
+
+    data_handler = None
+    results = None
+    test = None
+    theta = None
+    eta = None
+    pr = None
+    likelihood = None
+    prediction_matrix = None
+    rng = None
+
+    def __init__(self, user_groups, item_groups, iterations=400, sampling=1, seed=None,
+                 debug=False, backend="auto"):
+        self.start_time = datetime.now()
+        self.user_groups = user_groups
+        self.item_groups = item_groups
+        self.iterations = iterations
+        self.sampling = sampling
+        self.debug = debug
+        self.backend = backend
+
+        self.rng = np.random.default_rng(seed)
+        self.child_states = self.rng.bit_generator._seed_seq.spawn(sampling)
+
+        self.logger = setup_logger("MMSBM")
+
+        self._normalization_factors = None
+        self._engine = None
+        self._index_cache = None
+
+    # ------------------------------------------------------------------ preparation
+    def _prepare_objects(self, train):
+        """Sizes, degree factors and the on-device index structure
+        (replaces src/mmsbm.py:93-146; the O((U+I)N) scans become one GPU sort)."""
+        self.ratings = sorted(set(train[:, 2]))
+        self.r = max(self.ratings)
+        self.p = int(train[:, 0].max())
+        self.m = int(train[:, 1].max())
+        self.train = train
+        self._dims = {
+            'n_samples': len(train),
+            'n_user_groups': self.user_groups,
+            'n_item_groups': self.item_groups,
+            'n_ratings': len(self.ratings),
+        }
+        self.em = ExpectationMaximization(
+            dims=self._dims, user_indices=None, item_indices=None, rating_indices=None,
+            norm_factors=None, backend=self.backend, debug=self.debug)
+        self._engine = Engine(train, self.p + 1, self.m + 1, self._dims['n_ratings'],
+                              self.user_groups, self.item_groups)
+        du = np.maximum(self._engine.udeg.cpu().numpy()[:self.p + 1].astype(np.int64), 1)
+        di = np.maximum(self._engine.ideg.cpu().numpy()[:self.m + 1].astype(np.int64), 1)
+        self._normalization_factors = {
+            'user': np.repeat(du[:, None], self.user_groups, axis=1),
+            'item': np.repeat(di[:, None], self.item_groups, axis=1),
+        }
+        self.em._normalization_factors = self._normalization_factors
+        self._index_cache = None
+
+    def _index_lists(self):
+        """Per-id row lists of the reference (src/mmsbm.py:114-122), derived on demand
+        from the device index structure."""
+        if self._index_cache is None:
+            e, R = self._engine, self._dims['n_ratings']
+            out = {}
+            for name, seg, perm, n_ids in (("user", e.useg, e.uperm, e.U), ("item", e.iseg, e.iperm, e.I)):
+                seg, perm = seg.cpu().numpy(), perm.cpu().numpy()[:e.N]
+                out[name] = [np.sort(perm[seg[a * R]:seg[(a + 1) * R]]).astype(np.int64)
+                             for a in range(n_ids)]
+            seg, perm = e.useg.cpu().numpy(), e.uperm.cpu().numpy()[:e.N]
+            out["rating"] = [np.sort(np.concatenate(
+                [perm[seg[a * R + r]:seg[a * R + r + 1]] for a in range(e.U)] or [perm[:0]])).astype(np.int64)
+                for r in range(R)]
+            self._index_cache = out
+        return self._index_cache
+
+    @property
+    def _user_indices(self):
+        return None if self._engine is None else self._index_lists()["user"]
+
+    @property
+    def _item_indices(self):
+        return None if self._engine is None else self._index_lists()["item"]
+
+    @property
+    def _rating_indices(self):
+        return None if self._engine is None else self._index_lists()["rating"]
+
+    def _initial_parameters(self, seed):
+        """theta0, eta0, pr0 of one run: three draws in this order from
+        default_rng(seed) (src/mmsbm.py:224-233)."""
+        rng = np.random.default_rng(seed)
+        K, L, R = self.user_groups, self.item_groups, self._dims['n_ratings']
+        theta = self.em.normalize_with_d(rng.random((self.p + 1, K)), 'user')
+        eta = self.em.normalize_with_d(rng.random((self.m + 1, L)), 'item')
+        pr = self.em.normalize_with_self(rng.random((K, L, R)))
+        return theta, eta, pr
+
+    # -------------------------------------------------------------------------- fit
+    def _run_batch(self, engine, seeds, run_ids):
+        inits = [self._initial_parameters(s) for s in seeds]
+        engine.set_params(np.stack([a[0] for a in inits]), np.stack([a[1] for a in inits]),
+                          np.stack([a[2] for a in inits]))
+        if self.debug:
+            done = 0
+            while done < self.iterations:
+                step = 1 if done == 0 else min(50, self.iterations - done)
+                engine.run(step)
+                done += step
+                if (done - 1) % 50 == 0:
+                    for i, lik in zip(run_ids, engine.likelihood()):
+                        self.logger.debug(f"\nLikelihood at run {i} is {lik:.0f}")
+        else:
+            engine.run(self.iterations)
+        lik = engine.likelihood()
+        theta, eta, pr = engine.get_params()
+        return {i: {"likelihood": np.float64(lik[j]), "pr": pr[j], "theta": theta[j], "eta": eta[j]}
+                for j, i in enumerate(run_ids)}
+
+    def fit(self, data, silent=False):
+        """Fit ``sampling`` EM runs on a DataFrame with columns [users, items, ratings]."""
+        if not silent:
+            self.logger.info(f"Running {self.sampling} runs of {self.iterations} iterations.")
+        self.data_handler = DataHandler()
+        train = self.data_handler.format_train_data(data)
+        self._prepare_objects(train)
+        rank, world = dist_info()
+        mine = shard_runs(self.sampling, rank, world)
+        local = self._run_batch(self._engine, [self.child_states[i] for i in mine], mine) if mine else {}
+        self.results = gather_runs(local, self.sampling)
+
+    def run_one_sampling(self, data, seed, i):
+        """One EM run from ``seed`` on the encoded array ``data`` (in-process; the
+        reference's unit of work, src/mmsbm.py:187-269)."""
+        engine = self._engine
+        if engine is None or data is not self.train:
+            engine = Engine(data, self.p + 1, self.m + 1, self._dims['n_ratings'],
+                            self.user_groups, self.item_groups)
+        return self._run_batch(engine, [seed], [i])[i]
+
+    def _check_is_fitted(self):
+        assert self.results is not None, "You need to fit the model before predicting."
+
+    def _check_has_predictions(self):
+        assert self.prediction_matrix is not None, (
+            "You need to predict before computing the goodness of fit " "parameters.")
+
+    # ---------------------------------------------------------------------- predict
+    def predict(self, data):
+        """Rating distribution [M,R] for the rows of ``data`` (mean over runs); the best
+        run (highest accuracy on ``data``, first on ties) provides theta / eta / pr."""
+        self._check_is_fitted()
+        test = self.data_handler.format_test_data(data)
+        self.test = test
+
+        prs = np.array([a["pr"] for a in self.results])
+        likelihoods = np.array([a["likelihood"] for a in self.results])
+        thetas = np.array([a["theta"] for a in self.results])
+        etas = np.array([a["eta"] for a in self.results])
+
+        engine = self._engine
+        engine.set_params(thetas, etas, prs)
+        rat = engine.prod_dist_device(test)                   # [S,M,R] on the GPU
+        accuracies = [s["accuracy"] for s in predict_stats(rat, test[:, 2])]
+        best = accuracies.index(max(accuracies))
+
+        self.theta = self.data_handler.return_theta_indices(thetas[best])
+        self.eta = self.data_handler.return_eta_indices(etas[best])
+        self.pr = self.data_handler.return_pr_indices(prs[best])
+        self.likelihood = likelihoods[best]
+
+        self.prediction_matrix = engine.mean_over_runs(rat).cpu().numpy()
+        return self.prediction_matrix
+
+    def score(self, silent=False):
+        """{"stats": {accuracy, one_off_accuracy, mae, s2, s2pond, likelihood},
+        "objects": {theta, eta, pr}} for the last prediction."""
+        self._check_has_predictions()
+        stats = self._compute_stats(self.prediction_matrix)
+        stats["likelihood"] = self.likelihood
+        if not silent:
+            self.logger.debug(
+                f"Done {self.sampling} runs in {(datetime.now() - self.start_time).total_seconds() / 60.0:.2f} "
+                f"minutes.")
+            self.logger.info(
+                f"The final accuracy is {stats['accuracy']}, the one off accuracy is {stats['one_off_accuracy']} "
+                f"and the MAE is {stats['mae']}.")
+        return {"stats": stats, "objects": {"theta": self.theta, "eta": self.eta, "pr": self.pr}}
+
+    # ----------------------------------------------------------------------- cv_fit
+    def cv_fit(self, data, folds=5):
+        """k-fold cross-validation; returns the accuracy of every fold and keeps the
+        objects of the most accurate one (src/mmsbm.py:371-472)."""
+        items_per_fold = structure_folds(data, folds)
+        temp = data
+        all_results = []
+        for f in range(folds):
+            self.logger.info(f"Running fold {f + 1} of {folds}...")
+            # per user (groups in sorted key order), up to items_per_fold held-out rows;
+            # draws come from self.rng in that order.  Index label 0 is never held out
+            # (the reference filters str(a) != "0", src/mmsbm.py:435).
+            picked = []
+            for _, group in temp.groupby(temp.columns[0]):
+                chosen = get_n_per_group(group, n=items_per_fold, rng=self.rng)
+                picked.extend(chosen)
+            test_indices = [a for a in picked if str(a) != "0"]
+
+            test = temp.loc[test_indices, :]
+            train = data[~data.index.isin(test.index)]
+            temp = temp[~temp.index.isin(test_indices)]
+
+            self.fit(train, silent=True)
+            self.prediction_matrix = self.predict(test)
+            results = self.score(silent=True)
+            all_results.append({
+                "stats": results["stats"],
+                "objects": {"theta": self.theta, "eta": self.eta, "pr": self.pr,
+                            "rat": self.prediction_matrix},
+            })
+
+        accuracies = [a["stats"]["accuracy"] for a in all_results]
+        best = accuracies.index(max(accuracies))
+        self.theta = all_results[best]["objects"]["theta"]
+        self.eta = all_results[best]["objects"]["eta"]
+        self.pr = all_results[best]["objects"]["pr"]
+        self.prediction_matrix = all_results[best]["objects"]["rat"]
+
+        self.logger.info(f"Ran {folds} folds with accuracies {accuracies}.")
+        self.logger.info(f"They have mean {np.mean(accuracies)} and sd {np.std(accuracies)}.")
+        return accuracies
+
+    # ------------------------------------------------------------------------ stats
+    def choose_best_run(self, rats):
+        """Index of the run with the highest accuracy (first on ties)."""
+        accuracies = [self._compute_stats(a)["accuracy"] for a in rats]
+        return accuracies.index(max(accuracies))
+
+    def _compute_stats(self, rat):
+        """accuracy, one_off_accuracy, mae, s2, s2pond of one [M,R] distribution against
+        ``self.test`` -- an on-device reduction (src/mmsbm.py:480-539)."""
+        return predict_stats(rat, self.test[:, 2])[0]
+
+    def compute_likelihood(self, data, theta, eta, pr):
+        return self.em.compute_likelihood(data, theta, eta, pr)

@@ -1,0 +1,370 @@
+"""Parity of the CUDA path with the oracle and the reference's golden vectors.
+Everything here calls through the C ABI (host-pointer entry points via the plugin
+module, device-pointer entry points via Engine).  Needs a B200.
+
+Tolerances (BASELINE.json north_star): integer / index work bit-exact; theta, eta, pr
+<= 1e-10 relative per element after one iteration from identical inputs; likelihood
+<= 1e-8 relative; same best run.  The CUDA path reassociates the sums (em_step.cu
+header), so agreement is ~1e-14, far inside the budget; the tests assert the budget and
+print the observed error.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import mmsbm_oracle as orc
+from tests.util import mock_data, random_params, random_triples, rel_err
+
+pytestmark = pytest.mark.gpu
+
+PARAM_TOL = 1e-10
+LIK_TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def kb():
+    from mmsbm_b200 import kernels_b200
+    return kernels_b200
+
+
+def _gold(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+# ----------------------------------------------------------------- plugin (b1) level
+def test_toy_backends_like_the_reference_test(kb, golden_dir):
+    """tests/test_backends.py:7-60 of the reference, with 'b200' as the alternative backend."""
+    g = _gold(golden_dir, "toy_backends.npz")
+    for tag in ("omega", "prod"):
+        args = [g[f"{tag}_{k}"] for k in ("data", "theta", "eta", "pr")]
+        out = kb.compute_omegas(*args)
+        assert np.allclose(out, g[f"{tag}_omegas_numpy"], atol=1e-8)
+        np.testing.assert_array_equal(out, g[f"{tag}_omegas_numpy"])     # same product order: bit-exact
+        dist = kb.prod_dist(*args)
+        assert np.allclose(dist, g[f"{tag}_prod_numpy"], atol=1e-8)
+        assert rel_err(dist, g[f"{tag}_prod_numpy"]) < 1e-13
+        nt, ne, npr = kb.update_coefficients(*args)
+        assert rel_err(nt, g[f"{tag}_ntheta"]) < PARAM_TOL
+        assert rel_err(ne, g[f"{tag}_neta"]) < PARAM_TOL
+        assert rel_err(npr, g[f"{tag}_npr"]) < PARAM_TOL
+
+
+@pytest.mark.parametrize("name,tags", [("medium.npz", [""]), ("wide.npz", ["k20_", "l32_", "odd_"])])
+def test_update_coefficients_against_reference_golden(kb, golden_dir, name, tags):
+    g = _gold(golden_dir, name)
+    for t in tags:
+        data, theta, eta, pr = (g[t + k] for k in ("data", "theta", "eta", "pr"))
+        nt, ne, npr = kb.update_coefficients(data, theta, eta, pr)
+        errs = (rel_err(nt, g[t + "ntheta"]), rel_err(ne, g[t + "neta"]), rel_err(npr, g[t + "npr"]))
+        print(name, t, "rel err n_theta/n_eta/n_pr", errs)
+        assert max(errs) < PARAM_TOL
+        lik = kb.likelihood(data, theta, eta, pr)
+        assert abs(lik - g[t + "likelihood"]) <= LIK_TOL * abs(g[t + "likelihood"])
+        assert abs(lik - g[t + "likelihood"]) <= 1e-12 * abs(g[t + "likelihood"])
+        assert rel_err(kb.prod_dist(data[:257], theta, eta, pr), g[t + "prod"]) < 1e-12
+        om = kb.compute_omegas(data[:300], theta, eta, pr)
+        np.testing.assert_array_equal(om, orc.omegas(data[:300], theta, eta, pr))
+
+
+def test_empty_rating_level_and_zero_rows(kb):
+    """A level with no rows keeps a zero slab (src/kernels_numpy.py:74-77); an all-zero
+    theta row gives sum_omega = 0 -> divided by eps, contributing exactly zero."""
+    data = np.array([[0, 0, 0], [1, 1, 2], [1, 0, 2], [2, 1, 0]], dtype=np.int64)
+    g = np.random.default_rng(3)
+    theta, eta, pr = g.random((3, 3)), g.random((2, 2)), g.random((3, 2, 3))
+    theta[2] = 0.0
+    nt, ne, npr = kb.update_coefficients(data, theta, eta, pr)
+    rt, re_, rpr = orc.em_sums(data, theta, eta, pr)
+    assert np.all(npr[:, :, 1] == 0) and np.all(nt[2] == 0)
+    assert rel_err(nt, rt) < PARAM_TOL and rel_err(ne, re_) < PARAM_TOL and rel_err(npr, rpr) < PARAM_TOL
+
+
+def test_bad_ids_raise(kb):
+    from mmsbm_b200._lib import MmsbmError
+    theta, eta, pr = random_params(0, 3, 3, 2, 2, 2)
+    with pytest.raises(MmsbmError):
+        kb.update_coefficients(np.array([[0, 5, 0]], dtype=np.int64), theta, eta, pr)
+    with pytest.raises(MmsbmError):
+        kb.update_coefficients(np.array([[0, 0, 2]], dtype=np.int64), theta, eta, pr)
+
+
+# ------------------------------------------------------------------ index structure (a8)
+@pytest.mark.parametrize("shape", [(100, 5, 10, 5), (1, 1, 1, 1), (5000, 300, 7, 3), (70000, 2000, 900, 5),
+                                   (300000, 50, 40000, 11)])
+@pytest.mark.parametrize("heavy", [False, True])
+def test_index_build_bit_exact(shape, heavy):
+    from mmsbm_b200.engine import Engine
+    N, U, I, R = shape
+    if heavy and N < 1000:
+        pytest.skip("tiny")
+    data = random_triples(17, N, U, I, R, heavy_tail=heavy)
+    e = Engine(data, U, I, R, 2, 2)
+    for col, seg, adj, perm, deg, n_ids in ((0, e.useg, e.uadj, e.uperm, e.udeg, U),
+                                            (1, e.iseg, e.iadj, e.iperm, e.ideg, I)):
+        rseg, rperm = orc.bucket_order(data[:, col], data[:, 2], n_ids, R)
+        np.testing.assert_array_equal(seg.cpu().numpy()[:n_ids * R + 1], rseg)
+        np.testing.assert_array_equal(perm.cpu().numpy()[:N], rperm)
+        np.testing.assert_array_equal(adj.cpu().numpy()[:N], data[rperm, 1 - col].astype(np.int32))
+        np.testing.assert_array_equal(deg.cpu().numpy()[:n_ids], np.bincount(data[:, col], minlength=n_ids))
+
+
+def test_index_lists_match_reference_lists(golden_dir):
+    """MMSBM._user_indices/_item_indices/_rating_indices == the reference's np.where lists."""
+    from mmsbm_b200 import MMSBM
+    g = _gold(golden_dir, "fixture.npz")
+    mm = MMSBM(2, 2, iterations=1, seed=1)
+    mm._prepare_objects(g["train"])
+    for key, got in (("user", mm._user_indices), ("item", mm._item_indices), ("rating", mm._rating_indices)):
+        want = np.split(g[f"{key}_index_concat"], np.cumsum(g[f"{key}_index_len"])[:-1])
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(mm._normalization_factors["user"], g["norm_user"])
+    np.testing.assert_array_equal(mm._normalization_factors["item"], g["norm_item"])
+
+
+# ------------------------------------------------------------- device engine (a2-a5, a7)
+def test_fixture_one_and_ten_iterations(golden_dir):
+    from mmsbm_b200.engine import Engine
+    g = _gold(golden_dir, "fixture.npz")
+    e = Engine(g["train"], 5, 10, 5, 2, 2)
+    e.set_params(g["theta0"], g["eta0"], g["pr0"])
+    e.run(1)
+    th, et, pr = e.get_params()
+    errs = (rel_err(th[0], g["theta1"]), rel_err(et[0], g["eta1"]), rel_err(pr[0], g["pr1"]))
+    print("fixture, 1 iteration:", errs)
+    assert max(errs) < PARAM_TOL
+    assert abs(e.likelihood()[0] - g["likelihood1"]) <= LIK_TOL * abs(g["likelihood1"])
+    e.run(9)
+    th, et, pr = e.get_params()
+    errs = (rel_err(th[0], g["theta10"]), rel_err(et[0], g["eta10"]), rel_err(pr[0], g["pr10"]))
+    print("fixture, 10 iterations:", errs)
+    assert max(errs) < 1e-9
+    lik = e.likelihood()[0]
+    assert abs(lik - g["likelihood10"]) <= LIK_TOL * abs(g["likelihood10"])
+
+
+@pytest.mark.parametrize("K,L,R,S", [(10, 10, 5, 3), (20, 20, 5, 2), (7, 5, 4, 1), (3, 32, 6, 2), (33, 9, 5, 1),
+                                     (1, 1, 2, 1), (64, 48, 5, 1)])
+@pytest.mark.parametrize("heavy", [False, True])
+def test_batched_runs_one_iteration_vs_oracle(K, L, R, S, heavy):
+    from mmsbm_b200.engine import Engine
+    N, U, I = 60000, 700, 450
+    data = random_triples(23, N, U, I, R, heavy_tail=heavy)
+    theta, eta, pr = random_params(29, U, I, K, L, R, S=S)
+    e = Engine(data, U, I, R, K, L)
+    e.set_params(theta, eta, pr)
+    e.run(1)
+    th, et, prn = e.get_params()
+    lik = e.likelihood()
+    fu, fi = orc.degree_factors(data, K, L)
+    worst = 0.0
+    for s in range(S):
+        rt, re_, rp = orc.em_iteration(data, theta[s], eta[s], pr[s], fu, fi, chunk=20000)
+        worst = max(worst, rel_err(th[s], rt), rel_err(et[s], re_), rel_err(prn[s], rp))
+        want = sum(orc.likelihood(data[lo:lo + 20000], rt, re_, rp) for lo in range(0, N, 20000))
+        assert abs(lik[s] - want) <= LIK_TOL * abs(want)
+        # size-independent invariants of one EM step
+        np.testing.assert_allclose(th[s].sum(axis=1), 1.0, rtol=1e-12)
+        np.testing.assert_allclose(et[s].sum(axis=1), 1.0, rtol=1e-12)
+        np.testing.assert_allclose(prn[s].sum(axis=2), 1.0, rtol=1e-12)
+    print(f"K={K} L={L} R={R} S={S} heavy={heavy}: worst rel err {worst:.3e}")
+    assert worst < PARAM_TOL
+
+
+def test_raw_sums_flags_and_finalize():
+    """RAW flags give the unnormalised numerators; finalize = the post-all-reduce epilogue."""
+    from mmsbm_b200 import _lib
+    from mmsbm_b200.engine import Engine
+    N, U, I, K, L, R = 20000, 300, 200, 6, 9, 5
+    data = random_triples(31, N, U, I, R)
+    theta, eta, pr = random_params(37, U, I, K, L, R, S=2)
+    e = Engine(data, U, I, R, K, L)
+    e.set_params(theta, eta, pr)
+    th, et, prn = (t.clone() for t in e.step_raw(_lib.RAW_THETA | _lib.RAW_ETA_PR))
+    for s in range(2):
+        rt, re_, rp = orc.em_sums(data, theta[s], eta[s], pr[s])
+        assert rel_err(th[s].cpu().numpy()[:, :K], rt) < PARAM_TOL
+        assert rel_err(et[s].cpu().numpy()[:, :L], re_) < PARAM_TOL
+        assert rel_err(prn[s].cpu().numpy(), rp) < PARAM_TOL
+        assert abs(rp.sum() - N) < 1e-6                       # every rating distributes mass 1
+    e.finalize(et, prn)
+    fu, fi = orc.degree_factors(data, K, L)
+    for s in range(2):
+        _, re_, rp = orc.em_iteration(data, theta[s], eta[s], pr[s], fu, fi)
+        assert rel_err(et[s].cpu().numpy()[:, :L], re_) < PARAM_TOL
+        assert rel_err(prn[s].cpu().numpy(), rp) < PARAM_TOL
+
+
+def test_reproducible_bits():
+    """Fixed summation order: two runs of the same step give identical bits."""
+    from mmsbm_b200.engine import Engine
+    data = random_triples(41, 50000, 400, 300, 5, heavy_tail=True)
+    theta, eta, pr = random_params(43, 400, 300, 10, 10, 5, S=2)
+    outs = []
+    for _ in range(2):
+        e = Engine(data, 400, 300, 5, 10, 10)
+        e.set_params(theta, eta, pr)
+        e.run(3)
+        outs.append(e.get_params() + (e.likelihood(),))
+    for a, b in zip(*outs):
+        np.testing.assert_array_equal(a, b)
+
+
+# ------------------------------------------------------------------- predict / stats (a6, a10)
+def test_predict_stats_vs_oracle():
+    from mmsbm_b200.engine import predict_stats
+    g = np.random.default_rng(47)
+    M, R, S = 5000, 5, 3
+    rat = g.random((S, M, R))
+    rat /= rat.sum(axis=2, keepdims=True)
+    rat[0, :50] = 0.0                       # rows without prediction are dropped
+    rat[1, 100:120] = 0.2                   # exact ties -> first maximum
+    rat[2, 200, :] = [0, 0.5, 0, 0.5, 0]    # E[r] = 2 exactly; also a tie
+    rat[2, 201, :] = [0.5, 0.5, 0, 0, 0]    # E[r] = 0.5 -> rounds half to even (0)
+    real = g.integers(0, R, M)
+    stats, pred = predict_stats(rat, real, want_pred=True)
+    for s in range(S):
+        want = orc.prediction_stats(rat[s], real, list(range(R)))
+        np.testing.assert_array_equal(pred[s], np.argmax(rat[s], axis=1))      # bit-exact predictions
+        for k in ("accuracy", "one_off_accuracy", "mae"):
+            assert stats[s][k] == want[k], k
+        assert int(stats[s]["s2"]) == int(want["s2"])
+        assert abs(stats[s]["s2pond"] - want["s2pond"]) <= 1e-12 * want["s2pond"]
+
+
+def test_mmsbm_fixture_known_answers(golden_dir, tmp_path, monkeypatch):
+    """The reference's own end-to-end tests (tests/test_mmsbm.py:53-102) on this package."""
+    monkeypatch.chdir(tmp_path)
+    from mmsbm_b200 import MMSBM
+    meta = json.load(open(os.path.join(golden_dir, "fixture.json")))
+    g = _gold(golden_dir, "fixture.npz")
+    mm = MMSBM(2, 2, iterations=10, seed=1)
+    mm.fit(mock_data(1))
+    pred = mm.predict(mock_data(2))
+    sc = mm.score(silent=True)
+    assert pred.sum() == pytest.approx(100, 0.01)
+    assert rel_err(pred, g["prediction"]) < 1e-9
+    st = sc["stats"]
+    assert st["accuracy"] == pytest.approx(0.13, 0.01)
+    assert st["one_off_accuracy"] == pytest.approx(0.55, 0.01)
+    assert st["mae"] == pytest.approx(0.78, 0.01)
+    assert st["s2"] == 153
+    assert st["s2pond"] == pytest.approx(129.4766730930339, rel=1e-9)
+    assert st["likelihood"] == pytest.approx(-13.773187406968459, rel=LIK_TOL)
+    for k in ("accuracy", "one_off_accuracy", "mae", "s2"):
+        assert float(st[k]) == meta["stats"][k]
+    assert sc["objects"]["theta"].sum(axis=0)[0] == pytest.approx(meta["theta_col0_sum"], rel=1e-9)
+    assert sc["objects"]["eta"].sum(axis=0)[0] == pytest.approx(meta["eta_col0_sum"], rel=1e-9)
+    assert set(sc["objects"]["pr"].keys()) == {"1", "2", "3", "4", "5"}
+    assert [float(a.sum().sum()) for a in sc["objects"]["pr"].values()] == pytest.approx(meta["pr_sums"], rel=1e-9)
+    assert list(sc["objects"]["theta"].index) == meta["theta_index"]
+    assert rel_err(mm.results[0]["theta"], g["theta10"]) < 1e-9
+    assert mm.score(silent=False)["stats"]["accuracy"] == st["accuracy"]     # logging branch
+
+
+def test_mmsbm_best_run_choice(golden_dir, tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    from mmsbm_b200 import MMSBM
+    g = _gold(golden_dir, "sampling3.npz")
+    mm = MMSBM(2, 2, iterations=10, sampling=3, seed=1)
+    mm.fit(mock_data(1), silent=True)
+    pred = mm.predict(mock_data(2))
+    for s in range(3):
+        assert rel_err(mm.results[s]["theta"], g["thetas"][s]) < 1e-9
+        assert abs(mm.results[s]["likelihood"] - g["likelihoods"][s]) <= LIK_TOL * abs(g["likelihoods"][s])
+    rats = [mm.em.compute_prod_dist(mm.test, a["theta"], a["eta"], a["pr"]) for a in mm.results]
+    assert [mm._compute_stats(a)["accuracy"] for a in rats] == g["accuracies"].tolist()
+    assert mm.choose_best_run(rats) == int(g["best"]) == 1
+    assert mm.likelihood == pytest.approx(float(g["likelihoods"][1]), rel=LIK_TOL)
+    assert rel_err(pred, g["prediction"]) < 1e-9
+    stats = mm.score(silent=True)["stats"]
+    want = dict(zip(g["stats_keys"].tolist(), g["stats_vals"].tolist()))
+    for k in ("accuracy", "one_off_accuracy", "mae", "s2"):
+        assert float(stats[k]) == want[k]
+
+
+def test_mmsbm_cv_fit(golden_dir, tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    from mmsbm_b200 import MMSBM
+    want = json.load(open(os.path.join(golden_dir, "cvfit.json")))
+    mm = MMSBM(2, 2, iterations=10, seed=1)
+    acc = mm.cv_fit(mock_data(1), folds=2)
+    assert acc[0] == pytest.approx(0.125, 0.01) and acc[1] == pytest.approx(0.16, 0.01)
+    assert [float(a) for a in acc] == want["accuracies"]
+    np.testing.assert_array_equal(np.asarray(mm.test), np.asarray(want["final_test"]))
+
+
+def test_api_guards_and_helpers(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    from mmsbm_b200 import MMSBM
+    from mmsbm_b200.data_handler import DataHandler
+    with pytest.raises(AssertionError):
+        MMSBM(2, 2, seed=1).predict(mock_data(0))
+    with pytest.raises(AssertionError):
+        MMSBM(2, 2, seed=1).score()
+    mm = MMSBM(1, 1, seed=1)
+    monkeypatch.setattr(mm, "_compute_stats", lambda x: {"accuracy": x})
+    assert mm.choose_best_run([0.1, 0.7, 0.3]) == 1
+    mm = MMSBM(2, 2, iterations=1, sampling=1, seed=2)
+    train = DataHandler().format_train_data(mock_data(2, n=15))
+    mm._prepare_objects(train)
+    res = mm.run_one_sampling(train, seed=123, i=0)
+    assert set(res) == {"likelihood", "pr", "theta", "eta"} and res["pr"].shape[:2] == (2, 2)
+    want = orc.run_em(train, 123, 2, 2, 1)
+    assert rel_err(res["theta"], want["theta"]) < PARAM_TOL
+    assert np.isfinite(mm.compute_likelihood(mm.train, res["theta"], res["eta"], res["pr"]))
+
+
+def test_reference_loader_contract():
+    """load_backend returns the reference's 4-tuple; kernels_b200 at the repo root is the
+    module the REFERENCE's loader would import for backend='b200'."""
+    import kernels_b200 as plugin
+    from mmsbm_b200 import load_backend
+    co, uc, pdist, name = load_backend("auto")
+    assert name == "b200" and co is plugin.compute_omegas and uc is plugin.update_coefficients
+    with pytest.raises(ImportError):
+        load_backend("numpy")
+
+
+# ------------------------------------------------------- full-size properties (BASELINE shapes)
+@pytest.mark.parametrize("shape", [
+    dict(name="ML-1M", N=1_000_000, U=6040, I=3706, K=10, L=10, S=8),
+    dict(name="ML-20M", N=20_000_000, U=138_000, I=27_000, K=20, L=20, S=2),
+])
+def test_full_size_invariants(shape):
+    """At sizes the oracle cannot reach, check what must hold for any input: each rating
+    distributes unit mass (sum n_pr = N), theta rows sum to 1, eta rows sum to 1, pr sums
+    to 1 over ratings, and a subsample of users / items agrees with the oracle restricted to
+    their rows (theta_u' depends only on u's ratings)."""
+    from mmsbm_b200 import _lib
+    from mmsbm_b200.engine import Engine
+    N, U, I, K, L, S = (shape[k] for k in ("N", "U", "I", "K", "L", "S"))
+    R = 5
+    data = random_triples(53, N, U, I, R)
+    theta, eta, pr = random_params(59, U, I, K, L, R, S=S)
+    e = Engine(data, U, I, R, K, L)
+    e.set_params(theta, eta, pr)
+    raw = e.step_raw(_lib.RAW_THETA | _lib.RAW_ETA_PR)
+    npr = raw[2].cpu().numpy()
+    for s in range(S):
+        assert abs(npr[s].sum() - N) <= 1e-9 * N
+    nth = raw[0].cpu().numpy()[..., :K]
+    deg = np.bincount(data[:, 0], minlength=U)
+    np.testing.assert_allclose(nth.sum(axis=2), np.broadcast_to(deg, (S, U)), rtol=1e-11)
+    e.run(1)
+    th, et, prn = e.get_params()
+    np.testing.assert_allclose(th.sum(axis=2), 1.0, rtol=1e-11)
+    np.testing.assert_allclose(et.sum(axis=2), 1.0, rtol=1e-11)
+    np.testing.assert_allclose(prn.sum(axis=3), 1.0, rtol=1e-11)
+    users = np.array([0, 1, U // 2, U - 1])
+    rows = data[np.isin(data[:, 0], users)]
+    rt, _, _ = orc.em_sums(rows, theta[0], eta[0], pr[0])
+    assert rel_err(th[0][users] * np.maximum(deg[users], 1)[:, None], rt[users]) < PARAM_TOL
+    items = np.array([0, I // 3, I - 1])
+    rows = data[np.isin(data[:, 1], items)]
+    _, re_, _ = orc.em_sums(rows, theta[0], eta[0], pr[0])
+    degi = np.bincount(data[:, 1], minlength=I)
+    assert rel_err(et[0][items] * np.maximum(degi[items], 1)[:, None], re_[items]) < PARAM_TOL

@@ -1,0 +1,157 @@
+"""CPU tests of the host-side logic: encoding, fold construction, sharding helpers,
+the C-ABI library's exported symbols.  No GPU needed, no compute call made."""
+import ctypes
+import json
+import logging
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from mmsbm_b200 import _lib
+from mmsbm_b200.data_handler import DataHandler
+from mmsbm_b200.helpers import get_n_per_group, structure_folds
+from mmsbm_b200.parallel import shard_runs, user_partition
+from oracle import mmsbm_oracle as orc
+from tests.util import mock_data
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ C ABI
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "mmsbm_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(mmsbm_[a-z_0-9]+)\s*\(", header)))
+    assert declared, "no declarations found"
+    assert os.path.exists(_lib.LIB_PATH), "run `python -m mmsbm_b200.build` first"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert sorted(_lib.EXPORTS) == declared
+    assert lib.mmsbm_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a GPU the backend must raise ImportError (the reference's own signal,
+    src/backend.py:23-28), never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from mmsbm_b200.backend import load_backend
+    for name in ("auto", "b200", "numpy"):
+        with pytest.raises(ImportError):
+            load_backend(name)
+
+
+def test_product_code_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing shipped may import, link or call it."""
+    offenders = []
+    for top in ("mmsbm_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    for ln in open(os.path.join(dirpath, f)).read().splitlines():
+                        if "oracle" in ln and re.match(r"\s*(import|from|#include)\b", ln):
+                            offenders.append((f, ln.strip()))
+    src = open(os.path.join(ROOT, "kernels_b200.py")).read()
+    assert "oracle" not in src and not offenders, offenders
+
+
+# ---------------------------------------------------------------- encoding
+def test_encoding_matches_reference_golden(golden_dir):
+    enc = json.load(open(os.path.join(golden_dir, "encoding.json")))
+    df = pd.DataFrame({"users": [1, 10, 2, 100, 11, 10], "items": ["b", "a", "B", "10", "9", "a"],
+                       "ratings": [5.0, 1.0, 3.5, 10.0, 2.0, 1.0]})
+    dh = DataHandler()
+    out = dh.format_train_data(df)
+    assert out.dtype == np.int64 and out.tolist() == enc["train_out"]
+    assert [dh.obs_dict, dh.items_dict, dh.ratings_dict] == enc["dicts"]
+    tdf = pd.DataFrame({"users": [10, 7, 2, 100, 1], "items": ["a", "a", "zz", "9", "B"],
+                        "ratings": [1.0, 5.0, 3.5, 4.0, 10.0]})
+    assert dh.format_test_data(tdf).tolist() == enc["test_out"]
+
+
+def test_encoding_warnings(golden_dir, caplog):
+    enc = json.load(open(os.path.join(golden_dir, "encoding.json")))
+    dh = DataHandler()
+    dh.format_train_data(pd.DataFrame({"users": [1, 10, 2, 100, 11, 10],
+                                       "items": ["b", "a", "B", "10", "9", "a"],
+                                       "ratings": [5.0, 1.0, 3.5, 10.0, 2.0, 1.0]}))
+    log = logging.getLogger("MMSBM")
+    old = log.propagate
+    log.propagate = True
+    try:
+        with caplog.at_level(logging.WARNING, logger="MMSBM"):
+            dh.format_test_data(pd.DataFrame({"users": [10, 7, 2, 100, 1], "items": ["a", "a", "zz", "9", "B"],
+                                              "ratings": [1.0, 5.0, 3.5, 4.0, 10.0]}))
+    finally:
+        log.propagate = old
+    assert [r.getMessage() for r in caplog.records] == enc["test_warnings"]
+
+
+def test_encoding_fixture_and_large_int_path(golden_dir):
+    g = np.load(os.path.join(golden_dir, "fixture.npz"))
+    meta = json.load(open(os.path.join(golden_dir, "fixture.json")))
+    dh = DataHandler()
+    np.testing.assert_array_equal(dh.format_train_data(mock_data(1)), g["train"])
+    assert dh.obs_dict == meta["obs_dict"] and dh.ratings_dict == meta["ratings_dict"]
+    np.testing.assert_array_equal(dh.format_test_data(mock_data(2)), g["test"])
+    # the per-distinct-value fast path (>64 rows, integer dtype) against the oracle's per-cell str()
+    rng = np.random.default_rng(5)
+    df = pd.DataFrame({"users": rng.integers(0, 300, 5000), "items": rng.integers(0, 120, 5000).astype(str),
+                       "ratings": rng.integers(1, 11, 5000)})
+    out = DataHandler().format_train_data(df)
+    ref, _ = orc.encode_train(df["users"].tolist(), df["items"].tolist(), df["ratings"].tolist())
+    np.testing.assert_array_equal(out, ref)
+
+
+def test_stringdtype_columns():
+    s = pd.StringDtype()
+    df = pd.DataFrame({"users": pd.Series(["u1", "u2", "u1", "u3"], dtype=s),
+                       "items": pd.Series(["i1", "i2", "i1", "i3"], dtype=s),
+                       "ratings": pd.Series(["1", "2", "3", "1"], dtype=s)})
+    dh = DataHandler()
+    out = dh.format_train_data(df)
+    assert out.shape == (4, 3) and np.issubdtype(out.dtype, np.integer)
+    assert dh.format_test_data(df).shape == (4, 3)
+
+
+def test_decoding_round_trip():
+    dh = DataHandler()
+    dh.format_train_data(mock_data(1))
+    th = dh.return_theta_indices(np.zeros((5, 2)))
+    assert list(th.index) == [f"user{k}" for k in range(5)]
+    assert set(dh.return_pr_indices(np.zeros((2, 2, 5))).keys()) == {"1", "2", "3", "4", "5"}
+
+
+# ------------------------------------------------------------------- folds
+def test_fold_helpers():
+    df = mock_data(1)
+    assert structure_folds(df, 2) == 5
+    with pytest.raises(AssertionError):
+        structure_folds(df, 11)
+    rng = np.random.default_rng(0)
+    small = df.iloc[:3]
+    got = get_n_per_group(small, n=5, rng=rng)          # shrinks to the group size
+    assert sorted(got) == [0, 1, 2]
+    # a failed over-sized request consumes no random numbers in numpy's Generator.choice
+    a, b = np.random.default_rng(9), np.random.default_rng(9)
+    with pytest.raises(ValueError):
+        a.choice(np.arange(3), 5, replace=False)
+    assert a.random() == b.random()
+
+
+# ---------------------------------------------------------------- sharding
+def test_shard_runs_and_user_partition():
+    for world in (1, 2, 3, 8):
+        got = sorted(s for r in range(world) for s in shard_runs(8, r, world))
+        assert got == list(range(8))
+    deg = np.array([5, 1, 1, 1, 8, 2, 2, 10, 1, 1])
+    for world in (1, 2, 4, 8):
+        b = user_partition(deg, world)
+        assert b[0] == 0 and b[-1] == len(deg) and np.all(np.diff(b) >= 0) and len(b) == world + 1
+    b = user_partition(deg, 2)
+    left = deg[:b[1]].sum()
+    assert abs(left - deg.sum() / 2) <= deg.max()

@@ -1,0 +1,46 @@
+"""Seeded synthetic problems shared by the tests and the bench (no reference needed)."""
+import numpy as np
+import pandas as pd
+
+
+def mock_data(seed, n=100):
+    """The generator of the reference's own fixture (tests/test_mmsbm.py:12-22)."""
+    rng = np.random.default_rng(seed)
+    return pd.DataFrame({
+        "users": [f"user{rng.choice(list(range(5)))}" for _ in range(n)],
+        "items": [f"item{rng.choice(list(range(10)))}" for _ in range(n)],
+        "ratings": [rng.choice(list(range(1, 6))) for _ in range(n)],
+    })
+
+
+def random_triples(seed, N, U, I, R, heavy_tail=False):
+    """int64 [N,3]; every user / item / rating id appears at least once (N >= max(U,I,R))."""
+    g = np.random.default_rng(seed)
+    if heavy_tail:   # Zipf-like popularity, exponent ~1
+        pu = 1.0 / np.arange(1, U + 1); pu /= pu.sum()
+        pi = 1.0 / np.arange(1, I + 1); pi /= pi.sum()
+        u = g.choice(U, size=N, p=pu)
+        i = g.choice(I, size=N, p=pi)
+    else:
+        u = g.integers(0, U, N)
+        i = g.integers(0, I, N)
+    r = g.integers(0, R, N)
+    u[:U] = np.arange(U); i[:I] = np.arange(I); r[:R] = np.arange(R)
+    return np.stack([u, i, r], axis=1).astype(np.int64)
+
+
+def random_params(seed, U, I, K, L, R, S=None):
+    g = np.random.default_rng(seed)
+    lead = () if S is None else (S,)
+    theta = g.random(lead + (U, K)); eta = g.random(lead + (I, L)); pr = g.random(lead + (K, L, R))
+    theta /= theta.sum(axis=-1, keepdims=True)
+    eta /= eta.sum(axis=-1, keepdims=True)
+    pr /= pr.sum(axis=-1, keepdims=True)
+    return theta, eta, pr
+
+
+def rel_err(a, b):
+    """max over elements of |a-b| / max(|b|, tiny): the per-element relative error the
+    north_star tolerance (1e-10) is stated in."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))) if a.size else 0.0
