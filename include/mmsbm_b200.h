@@ -24,8 +24,8 @@
  *     host surface exactly as the reference's encoded ``data`` array;
  *   - parameters are float64.  Device layout for S runs (``sampling``):
  *         theta [S][U][ldk]   eta [S][I][ldl]   pr [S][K][L][R]
- *     with ldk = K rounded up to even, ldl likewise (rows are 16-byte multiples
- *     for 128-bit loads); padding columns must be zero.  Host layout is the
+ *     with ldk = mmsbm_row_stride(K) = K rounded up to a multiple of 4, ldl likewise
+ *     (rows are whole 32-byte chunks for 256-bit loads); padding columns must be zero.  Host layout is the
  *     reference's: theta [S][U][K], eta [S][I][L], pr [S][K][L][R], C order.
  *
  * Index structure ("graph"): rows grouped by (user, rating) and by
@@ -64,6 +64,8 @@ int         mmsbm_abi_version(void);
 const char* mmsbm_last_error(void);
 /* number of CUDA devices visible, or a negative code; never falls back to CPU */
 int         mmsbm_device_count(void);
+/* device row stride (in doubles) of a theta / eta row with k groups */
+int         mmsbm_row_stride(int32_t k);
 /* kernels launched by this library on the calling thread since it was loaded */
 int64_t     mmsbm_launch_count(void);
 

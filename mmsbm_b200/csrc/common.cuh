@@ -15,7 +15,8 @@ constexpr unsigned kFull = 0xffffffffu;
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
-inline int round_even(int x) { return (x + 1) & ~1; }
+// device row stride of theta / eta: rows are whole 32-byte chunks (256-bit loads)
+inline int row_stride(int x) { return (x + 3) & ~3; }
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 #define MMSBM_CUDA(expr)                                                              \

@@ -13,12 +13,12 @@
 //     n_pr[a][b][r] = P[a][b][r] * sum_segments own[a] g_r[b] (rank-1 update per segment)
 //
 // which is the reference's sum reassociated (agreement ~1e-15 relative, tests/test_em_gpu.py).
-// Per rating the kernel moves one neighbour row (8*NB bytes, 128-bit coalesced loads by a
+// Per rating the kernel moves one neighbour row (8*NB bytes, 256-bit coalesced loads by a
 // group of lanes) and 4 bytes of index; everything else stays in registers / shared memory.
 //
 // Mapping: one warp per segment; inside a warp, groups of G lanes own one rating each
-// (RPS = 32/G ratings per step), lane q of a group holds CH 16-byte chunks of the row
-// (chunk c*G+q).  S_n is a shuffle reduction over the group; g_r lives in registers and is
+// (RPS = 32/G ratings per step), lane q of a group holds CH 32-byte chunks of the row
+// (chunk c*G+q, fetched with one 256-bit load).  S_n is a shuffle reduction over the group; g_r lives in registers and is
 // reduced across groups once per (segment, rating level) -- rows are stored grouped by
 // rating level (include/mmsbm_b200.h) so the level is uniform except at group boundaries.
 // All sums have a fixed order: results are bit-reproducible run to run.
@@ -48,28 +48,61 @@ struct SegArgs {
   int G, RPS, normalize, segs_per_cta;
 };
 
-__host__ __device__ inline int ps_stride(int R, int NBp) { return (R * NBp) | 1; }
+// row stride of the staged P[a][r][b] table: R*NBp is a multiple of 4, +2 keeps rows 16-byte
+// aligned with APs/2 odd, so 128-bit reads of consecutive rows by consecutive lanes (the
+// epilogue) fall in distinct 16-byte banks
+__host__ __device__ inline int ps_stride(int R, int NBp) { return R * NBp + 2; }
 
-// shared-memory carve-up of the segment pass (all regions 16-byte aligned)
+// shared-memory carve-up of the segment pass (all regions 32-byte aligned)
 __host__ __device__ inline size_t ps_bytes(int NA, int R, int NBp) {
-  return ((size_t)NA * ps_stride(R, NBp) * 8 + 15) & ~(size_t)15;
+  return ((size_t)NA * ps_stride(R, NBp) * 8 + 31) & ~(size_t)31;
 }
 __host__ __device__ inline size_t warp_bytes(int NAp, int R, int NBp) {
-  return (size_t)(NAp + R * NBp) * 8 + (size_t)((R + 1 + 3) / 4 * 4) * 4;
+  return (size_t)(NAp + R * NBp) * 8 + (size_t)((R + 1 + 7) / 8 * 8) * 4;
 }
 inline size_t seg_smem_bytes(const SegArgs& a) {
-  return ps_bytes(a.NA, a.R, a.ldb) + kWarps * warp_bytes(a.lda, a.R, a.ldb) + 16;
+  return ps_bytes(a.NA, a.R, a.ldb) + kWarps * warp_bytes(a.lda, a.R, a.ldb) + 32;
+}
+
+struct alignas(16) double4_t { double x, y, z, w; };
+
+// one 256-bit read-only load (LDG.E.ENL2.256 on sm_100a): a lane's 32-byte chunk of a row
+__device__ __forceinline__ double4_t ldg256(const double* p) {
+  double4_t v;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ double4_t lds32(const double* p) {   // two 128-bit shared loads
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  const double2 b = *reinterpret_cast<const double2*>(p + 2);
+  return double4_t{a.x, a.y, b.x, b.y};
+}
+__device__ __forceinline__ void sts32(double* p, const double4_t& v) {
+  *reinterpret_cast<double2*>(p) = make_double2(v.x, v.y);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(v.z, v.w);
+}
+
+// 1/x for x in [eps, huge): MUFU.RCP64H seed (~2^-20) + two Newton steps -> <= ~1 ulp
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
 }
 
 template <int CH, int UN, bool EMIT>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, 2)
 segment_pass_kernel(const SegArgs A) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(32) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int run = blockIdx.y;
   const int R = A.R, NA = A.NA, NAp = A.lda, NBp = A.ldb;
   const int RNB = R * NBp, APs = ps_stride(R, NBp);
-  const int NCH = NBp >> 1;
+  const int NCH = NBp >> 2;                      // 32-byte chunks per neighbour row
   const int G = A.G, RPS = A.RPS;
 
   double* Ps = reinterpret_cast<double*>(smem_raw);                    // [NA][APs]
@@ -102,6 +135,15 @@ segment_pass_kernel(const SegArgs A) {
   const double* own_run = A.own + (size_t)run * A.nseg * NAp;
   const double* nbr_run = A.nbr + (size_t)run * A.nnbr * NBp;
   double* out_run = A.own_out + (size_t)run * A.nseg * NAp;
+  // lane-constant chunk offsets (in doubles) and validity
+  int coff[CH];
+  bool con[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int chunk = c * G + q;
+    con[c] = lane_on && chunk < NCH;
+    coff[c] = con[c] ? 4 * chunk : 0;
+  }
 
   for (;;) {
     int t = 0;
@@ -116,94 +158,120 @@ segment_pass_kernel(const SegArgs A) {
     for (int r = lane; r <= R; r += 32) bend[r] = __ldg(A.seg + (size_t)sg * R + r);
     __syncwarp();
 
-    // ---- w[r][b] = sum_a own[a] P[a][r][b] ----
-    for (int o = lane; o < RNB; o += 32) {
-      double acc = 0.0;
-      for (int a = 0; a < NA; ++a) acc = fma(own_s[a], Ps[a * APs + o], acc);
-      wg[o] = acc;
+    // ---- w[r][b] = sum_a own[a] P[a][r][b]: a lane owns output pairs, 128-bit reads ----
+    for (int o2 = lane; o2 < (RNB >> 1); o2 += 32) {
+      double2 acc = make_double2(0.0, 0.0);
+      const double* pcol = Ps + 2 * o2;
+      int a = 0;
+      for (; a + 1 < NA; a += 2) {
+        const double2 ow = *reinterpret_cast<const double2*>(own_s + a);
+        const double2 p0 = *reinterpret_cast<const double2*>(pcol + a * APs);
+        const double2 p1 = *reinterpret_cast<const double2*>(pcol + (a + 1) * APs);
+        acc.x = fma(ow.x, p0.x, acc.x); acc.y = fma(ow.x, p0.y, acc.y);
+        acc.x = fma(ow.y, p1.x, acc.x); acc.y = fma(ow.y, p1.y, acc.y);
+      }
+      if (a < NA) {
+        const double ow = own_s[a];
+        const double2 p0 = *reinterpret_cast<const double2*>(pcol + a * APs);
+        acc.x = fma(ow, p0.x, acc.x); acc.y = fma(ow, p0.y, acc.y);
+      }
+      *reinterpret_cast<double2*>(wg + 2 * o2) = acc;
     }
     __syncwarp();
 
     const int beg = bend[0], end = bend[R];
-    int r_mine = 0, cur_r = 0;
-    double2 g[CH];
+    int r_mine = 0, cur_r = 0, next_bound = bend[1];
+    double4_t g[CH], wr[CH];
 #pragma unroll
-    for (int c = 0; c < CH; ++c) g[c] = make_double2(0.0, 0.0);
+    for (int c = 0; c < CH; ++c) {
+      g[c] = double4_t{0.0, 0.0, 0.0, 0.0};
+      wr[c] = lds32(wg + coff[c]);
+    }
 
     auto flush = [&](int r) {
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
-        double2 v = g[c];
+        double4_t v = g[c];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
           if (off < RPS) {
-            double tx = __shfl_down_sync(kFull, v.x, off * G);
-            double ty = __shfl_down_sync(kFull, v.y, off * G);
-            if (grp + off < RPS) { v.x += tx; v.y += ty; }
+            const double tx = __shfl_down_sync(kFull, v.x, off * G);
+            const double ty = __shfl_down_sync(kFull, v.y, off * G);
+            const double tz = __shfl_down_sync(kFull, v.z, off * G);
+            const double tw = __shfl_down_sync(kFull, v.w, off * G);
+            if (grp + off < RPS) { v.x += tx; v.y += ty; v.z += tz; v.w += tw; }
           }
         }
-        const int chunk = c * G + q;
-        if (grp == 0 && chunk < NCH) *reinterpret_cast<double2*>(wg + r * NBp + 2 * chunk) = v;
-        g[c] = make_double2(0.0, 0.0);
+        if (grp == 0 && con[c]) sts32(wg + r * NBp + coff[c], v);
+        g[c] = double4_t{0.0, 0.0, 0.0, 0.0};
       }
     };
 
     for (int base = beg; base < end; base += UN * RPS) {
       int my_id = 0;
       if (lane < UN * RPS && base + lane < end) my_id = ld_stream(A.adj + base + lane);
-      double2 x[UN][CH];
+      double4_t x[UN][CH];
 #pragma unroll
       for (int un = 0; un < UN; ++un) {
         const int slot = un * RPS + grp;
-        const bool valid = lane_on && (base + slot < end);
+        const bool valid = base + slot < end;
         const int id = __shfl_sync(kFull, my_id, slot & 31);
-        const double2* row = reinterpret_cast<const double2*>(nbr_run + (size_t)id * NBp);
+        const double* row = nbr_run + (size_t)id * NBp;
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const int chunk = c * G + q;
-          x[un][c] = (valid && chunk < NCH) ? ldg2(row + chunk) : make_double2(0.0, 0.0);
-        }
+        for (int c = 0; c < CH; ++c)
+          x[un][c] = (valid && con[c]) ? ldg256(row + coff[c]) : double4_t{0.0, 0.0, 0.0, 0.0};
       }
 #pragma unroll
       for (int un = 0; un < UN; ++un) {
+        if (base + un * RPS >= end) break;  // warp-uniform
         const int j = base + un * RPS + grp;
         const bool valid = lane_on && (j < end);
-        if (base + un * RPS >= end) break;  // warp-uniform
-        if (valid) { while (j >= bend[r_mine + 1]) ++r_mine; }
+        if (valid && j >= next_bound) {     // rating level of this lane's row changes (rare)
+          do { ++r_mine; next_bound = bend[r_mine + 1]; } while (j >= next_bound);
+#pragma unroll
+          for (int c = 0; c < CH; ++c) wr[c] = lds32(wg + r_mine * NBp + coff[c]);
+        }
         double part = 0.0;
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
-          const int chunk = c * G + q;
-          if (chunk < NCH) {
-            const double2 w = *reinterpret_cast<const double2*>(wg + r_mine * NBp + 2 * chunk);
-            part = fma(x[un][c].x, w.x, part);
-            part = fma(x[un][c].y, w.y, part);
-          }
+          part = fma(x[un][c].x, wr[c].x, part);
+          part = fma(x[un][c].y, wr[c].y, part);
+          part = fma(x[un][c].z, wr[c].z, part);
+          part = fma(x[un][c].w, wr[c].w, part);
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
           if (off < G) {
-            double tp = __shfl_down_sync(kFull, part, off);
+            const double tp = __shfl_down_sync(kFull, part, off);
             if (q + off < G) part += tp;
           }
         }
         const double tot = __shfl_sync(kFull, part, grp * G);
-        const double inv = valid ? 1.0 / fmax(tot, kEps) : 0.0;
-        double2 val[CH];
+        // rows past the end carry x = 0, so their (finite) 1/eps never contributes
+        const double inv = fast_rcp(fmax(tot, kEps));
+        if (__all_sync(kFull, !valid || r_mine == cur_r)) {
 #pragma unroll
-        for (int c = 0; c < CH; ++c) val[c] = make_double2(x[un][c].x * inv, x[un][c].y * inv);
-        bool mine = valid && (r_mine == cur_r);
+          for (int c = 0; c < CH; ++c) {
+            g[c].x = fma(x[un][c].x, inv, g[c].x); g[c].y = fma(x[un][c].y, inv, g[c].y);
+            g[c].z = fma(x[un][c].z, inv, g[c].z); g[c].w = fma(x[un][c].w, inv, g[c].w);
+          }
+        } else {                            // a level boundary falls inside this step
+          double im = (valid && r_mine == cur_r) ? inv : 0.0;
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          g[c].x += mine ? val[c].x : 0.0;
-          g[c].y += mine ? val[c].y : 0.0;
-        }
-        while (__any_sync(kFull, valid && r_mine > cur_r)) {
-          flush(cur_r);
-          ++cur_r;
-          mine = valid && (r_mine == cur_r);
+          for (int c = 0; c < CH; ++c) {
+            g[c].x = fma(x[un][c].x, im, g[c].x); g[c].y = fma(x[un][c].y, im, g[c].y);
+            g[c].z = fma(x[un][c].z, im, g[c].z); g[c].w = fma(x[un][c].w, im, g[c].w);
+          }
+          while (__any_sync(kFull, valid && r_mine > cur_r)) {
+            flush(cur_r);
+            ++cur_r;
+            im = (valid && r_mine == cur_r) ? inv : 0.0;
 #pragma unroll
-          for (int c = 0; c < CH; ++c) g[c] = mine ? val[c] : make_double2(0.0, 0.0);
+            for (int c = 0; c < CH; ++c) {
+              g[c].x = x[un][c].x * im; g[c].y = x[un][c].y * im;
+              g[c].z = x[un][c].z * im; g[c].w = x[un][c].w * im;
+            }
+          }
         }
       }
     }
@@ -218,8 +286,14 @@ segment_pass_kernel(const SegArgs A) {
       double acc = 0.0;
       if (a < NA) {
         const double* prow = Ps + a * APs;
-        for (int o = 0; o < RNB; ++o) acc = fma(prow[o], wg[o], acc);
-        acc *= own_s[a];
+        double acc2 = 0.0;
+        for (int o = 0; o < RNB; o += 2) {
+          const double2 p = *reinterpret_cast<const double2*>(prow + o);
+          const double2 gv = *reinterpret_cast<const double2*>(wg + o);
+          acc = fma(p.x, gv.x, acc);
+          acc2 = fma(p.y, gv.y, acc2);
+        }
+        acc = (acc + acc2) * own_s[a];
         if (A.normalize) acc = acc / scale;
       }
       orow_out[a] = acc;
@@ -242,7 +316,7 @@ struct PrArgs {
 };
 
 __global__ void __launch_bounds__(kPrThreads) pr_accumulate_kernel(const PrArgs A) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(32) unsigned char smem_raw[];
   double* own_s = reinterpret_cast<double*>(smem_raw);   // [kPrBatch][NA]
   double* g_s = own_s + kPrBatch * A.NA;                 // [kPrBatch][RNB]
   const int run = blockIdx.y, slab = blockIdx.x;
@@ -352,23 +426,23 @@ static int env_int(const char* name, int dflt) {
 }
 
 static PassShape choose_shape(int NBp) {
-  const int NCH = NBp / 2;
-  int CH = 4;
-  for (int c = 1; c <= 4; c *= 2) {
+  // NCH 32-byte chunks per row are spread over G lanes x CH chunks per lane; G <= 8 keeps the
+  // per-rating shuffle reduction at <= 3 levels.  UN steps (RPS ratings each) are in flight.
+  const int NCH = NBp / 4;
+  int CH = 8;
+  for (int c = 1; c <= 8; c *= 2) {
     if ((NCH + c - 1) / c <= 8) { CH = c; break; }
   }
-  CH = env_int("MMSBM_CH", CH);
-  if (CH != 1 && CH != 2 && CH != 4) CH = 4;
+  int CHenv = env_int("MMSBM_CH", 0);
+  if ((CHenv == 1 || CHenv == 2 || CHenv == 4 || CHenv == 8) && (NCH + CHenv - 1) / CHenv <= 32) CH = CHenv;
   int G = (NCH + CH - 1) / CH;
   int Genv = env_int("MMSBM_G", 0);
   if (Genv >= G && Genv <= 32) G = Genv;
   int RPS = 32 / G;
-  int UN = 8 / CH;
+  int UN = CH >= 4 ? 1 : 4 / CH;
   while (UN > 1 && UN * RPS > 32) UN >>= 1;
   int UNenv = env_int("MMSBM_UN", 0);
-  if (UNenv == 1 || UNenv == 2 || UNenv == 4 || UNenv == 8) {
-    if (UNenv * CH <= 8 && UNenv * RPS <= 32) UN = UNenv;
-  }
+  if ((UNenv == 1 || UNenv == 2 || UNenv == 4) && UNenv * CH <= 4 && UNenv * RPS <= 32) UN = UNenv;
   return PassShape{CH, UN, G, RPS};
 }
 
@@ -387,9 +461,9 @@ static int launch_segment_pass(const SegArgs& a, const PassShape& sh, int n_runs
     MMSBM_LAUNCH_CHECK("segment_pass_kernel");                                                \
     return 0;                                                                                 \
   }
-  MMSBM_SEG_CASE(1, 1) MMSBM_SEG_CASE(1, 2) MMSBM_SEG_CASE(1, 4) MMSBM_SEG_CASE(1, 8)
-  MMSBM_SEG_CASE(2, 1) MMSBM_SEG_CASE(2, 2) MMSBM_SEG_CASE(2, 4)
-  MMSBM_SEG_CASE(4, 1) MMSBM_SEG_CASE(4, 2)
+  MMSBM_SEG_CASE(1, 1) MMSBM_SEG_CASE(1, 2) MMSBM_SEG_CASE(1, 4)
+  MMSBM_SEG_CASE(2, 1) MMSBM_SEG_CASE(2, 2)
+  MMSBM_SEG_CASE(4, 1) MMSBM_SEG_CASE(8, 1)
 #undef MMSBM_SEG_CASE
   set_error("no segment-pass variant for CH=%d UN=%d", sh.CH, sh.UN);
   return MMSBM_ERANGE;
@@ -413,7 +487,7 @@ struct EmDims {
 static EmDims em_dims(int U, int I, int R, int K, int L, int S) {
   EmDims d;
   d.U = U; d.I = I; d.R = R; d.K = K; d.L = L; d.S = S;
-  d.ldk = round_even(K); d.ldl = round_even(L);
+  d.ldk = row_stride(K); d.ldl = row_stride(L);
   d.emit_items = (I <= U);
   d.nseg_e = d.emit_items ? I : U;
   d.NA_e = d.emit_items ? L : K;
@@ -570,7 +644,7 @@ extern "C" int mmsbm_em_finalize(double* eta, const int32_t* ideg, int32_t I, in
   MMSBM_REQUIRE(eta && ideg && pr && I > 0 && L > 0 && K > 0 && R > 0 && S > 0, MMSBM_EINVAL,
                 "mmsbm_em_finalize: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int ldl = round_even(L);
+  const int ldl = row_stride(L);
   size_t total = (size_t)S * I * ldl;
   finalize_eta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(eta, ideg, I, ldl, L, total);
   MMSBM_LAUNCH_CHECK("finalize_eta_kernel");

@@ -97,7 +97,7 @@ static int upload_triples(Scope& sc, const int64_t* data, int64_t N, int U, int 
 
 // host compact [rows][w] -> device padded [rows][ld]
 static int upload_rows(Scope& sc, const double* src, size_t rows, int w, double** out) {
-  const int ld = round_even(w);
+  const int ld = row_stride(w);
   TRY(sc.alloc(out, rows * ld));
   if (ld == w) {
     MMSBM_CUDA(cudaMemcpyAsync(*out, src, rows * w * 8, cudaMemcpyHostToDevice, sc.st));
@@ -112,7 +112,7 @@ static int upload_rows(Scope& sc, const double* src, size_t rows, int w, double*
 }
 
 static int download_rows(Scope& sc, const double* dev, size_t rows, int w, double* dst) {
-  const int ld = round_even(w);
+  const int ld = row_stride(w);
   if (ld == w) {
     MMSBM_CUDA(cudaMemcpyAsync(dst, dev, rows * w * 8, cudaMemcpyDeviceToHost, sc.st));
     return 0;
@@ -154,6 +154,7 @@ using namespace mmsbm;
 extern "C" int mmsbm_abi_version(void) { return MMSBM_ABI_VERSION; }
 extern "C" const char* mmsbm_last_error(void) { return g_err; }
 extern "C" int64_t mmsbm_launch_count(void) { return g_launches; }
+extern "C" int mmsbm_row_stride(int32_t k) { return row_stride(k); }
 extern "C" int mmsbm_device_count(void) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -192,7 +193,7 @@ extern "C" int mmsbm_host_update_coefficients(const int64_t* data, int64_t N, co
   Scope sc; TRY(sc.open());
   DevTriples t; TRY(upload_triples(sc, data, N, U, I, R, &t));
   DevGraph g; TRY(build_graph(sc, t, N, U, I, R, &g));
-  const int ldk = round_even(K), ldl = round_even(L);
+  const int ldk = row_stride(K), ldl = row_stride(L);
   double *dth, *det, *dpr, *oth, *oet, *opr;
   TRY(upload_rows(sc, theta, (size_t)U, K, &dth));
   TRY(upload_rows(sc, eta, (size_t)I, L, &det));
@@ -262,7 +263,7 @@ extern "C" int mmsbm_host_fit(const int64_t* data, int64_t N, int32_t U, int32_t
   Scope sc; TRY(sc.open());
   DevTriples t; TRY(upload_triples(sc, data, N, U, I, R, &t));
   DevGraph g; TRY(build_graph(sc, t, N, U, I, R, &g));
-  const int ldk = round_even(K), ldl = round_even(L);
+  const int ldk = row_stride(K), ldl = row_stride(L);
   const size_t prn = (size_t)S * K * L * R;
   double *tha, *eta_a, *pra, *thb, *etb, *prb, *dlik;
   TRY(upload_rows(sc, theta0, (size_t)S * U, K, &tha));

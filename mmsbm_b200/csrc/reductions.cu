@@ -255,7 +255,7 @@ extern "C" int mmsbm_likelihood(const int32_t* useg, const int32_t* uadj, int64_
   const int nw = kLikCtas * kLikWarps;
   double* partial = arena.take<double>((size_t)S * nw);
   MMSBM_REQUIRE(partial, MMSBM_ENOMEM, "mmsbm_likelihood: workspace too small");
-  LikArgs a{useg, uadj, theta, eta, pr, partial, U, I, R, K, L, round_even(K), round_even(L)};
+  LikArgs a{useg, uadj, theta, eta, pr, partial, U, I, R, K, L, row_stride(K), row_stride(L)};
   size_t smem = ((size_t)R * K * L + (size_t)kLikWarps * K) * 8;
   MMSBM_REQUIRE(smem <= 227 * 1024, MMSBM_ERANGE, "mmsbm_likelihood: K*L*R too large for shared memory");
   MMSBM_CUDA(cudaFuncSetAttribute(likelihood_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -276,7 +276,7 @@ extern "C" int mmsbm_prod_dist(const int32_t* user, const int32_t* item, int64_t
                 "mmsbm_prod_dist: bad size");
   if (M == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  ProdArgs a{user, item, theta, eta, pr, rat, M, U, I, R, K, L, round_even(K), round_even(L)};
+  ProdArgs a{user, item, theta, eta, pr, rat, M, U, I, R, K, L, row_stride(K), row_stride(L)};
   size_t smem = ((size_t)R * K * L + 8 * (size_t)K) * 8;
   MMSBM_REQUIRE(smem <= 227 * 1024, MMSBM_ERANGE, "mmsbm_prod_dist: K*L*R too large for shared memory");
   MMSBM_CUDA(cudaFuncSetAttribute(prod_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -329,7 +329,7 @@ extern "C" int mmsbm_compute_omegas(const int32_t* user, const int32_t* item, co
   if (N == 0) return 0;
   const int64_t total = N * K * L;
   omegas_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      user, item, level, total, K, L, R, round_even(K), round_even(L), theta, eta, pr, omegas);
+      user, item, level, total, K, L, R, row_stride(K), row_stride(L), theta, eta, pr, omegas);
   MMSBM_LAUNCH_CHECK("omegas_kernel");
   return 0;
 }

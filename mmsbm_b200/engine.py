@@ -14,9 +14,6 @@ import torch
 from . import _lib
 
 
-def _even(x):
-    return (x + 1) & ~1
-
 
 class Engine:
     def __init__(self, data, n_users, n_items, n_levels, K, L, device=None):
@@ -31,7 +28,7 @@ class Engine:
             raise ValueError("data must have shape [N,3]")
         self.N = int(data.shape[0])
         self.U, self.I, self.R, self.K, self.L = int(n_users), int(n_items), int(n_levels), int(K), int(L)
-        self.ldk, self.ldl = _even(self.K), _even(self.L)
+        self.ldk, self.ldl = self.lib.mmsbm_row_stride(self.K), self.lib.mmsbm_row_stride(self.L)
         if self.N:
             lo, hi = data.min(axis=0), data.max(axis=0)
             if lo.min() < 0 or hi[0] >= self.U or hi[1] >= self.I or hi[2] >= self.R:
