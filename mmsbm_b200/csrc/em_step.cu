@@ -94,6 +94,14 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return fma(r, e, r);
 }
 
+// predicated 256-bit load: registers keep their (finite) previous contents when !pred
+__device__ __forceinline__ void ldg256_if(double4_t& v, const double* p, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "@p ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];\n\t}"
+      : "+d"(v.x), "+d"(v.y), "+d"(v.z), "+d"(v.w) : "l"(p), "r"((int)pred));
+}
+
 template <int CH, int UN, bool EMIT>
 __global__ void __launch_bounds__(kWarps * 32, 2)
 segment_pass_kernel(const SegArgs A) {
@@ -104,6 +112,7 @@ segment_pass_kernel(const SegArgs A) {
   const int RNB = R * NBp, APs = ps_stride(R, NBp);
   const int NCH = NBp >> 2;                      // 32-byte chunks per neighbour row
   const int G = A.G, RPS = A.RPS;
+  const int SLOTS = UN * RPS;                    // ratings per chunk of work (<= 32)
 
   double* Ps = reinterpret_cast<double*>(smem_raw);                    // [NA][APs]
   const size_t per_warp = warp_bytes(NAp, R, NBp);
@@ -115,7 +124,7 @@ segment_pass_kernel(const SegArgs A) {
 
   // ---- stage P[a][r][b] (zero padded) ----
   for (int t = threadIdx.x; t < NA * APs; t += blockDim.x) Ps[t] = 0.0;
-  if (threadIdx.x == 0) *ctr = 0;
+  if (threadIdx.x == 0) *ctr = kWarps;           // warps start on segments 0..kWarps-1
   __syncthreads();
   {
     const double* prs = A.pr + (size_t)run * A.K * A.L * R;
@@ -135,7 +144,8 @@ segment_pass_kernel(const SegArgs A) {
   const double* own_run = A.own + (size_t)run * A.nseg * NAp;
   const double* nbr_run = A.nbr + (size_t)run * A.nnbr * NBp;
   double* out_run = A.own_out + (size_t)run * A.nseg * NAp;
-  // lane-constant chunk offsets (in doubles) and validity
+  // lane-constant chunk offsets (in doubles), validity, and the add mask of the 3-level
+  // shuffle reduction over a group (G <= 8): bit `off` set iff lane q adds lane q+off
   int coff[CH];
   bool con[CH];
 #pragma unroll
@@ -144,49 +154,77 @@ segment_pass_kernel(const SegArgs A) {
     con[c] = lane_on && chunk < NCH;
     coff[c] = con[c] ? 4 * chunk : 0;
   }
+  int addm = 0;
+#pragma unroll
+  for (int off = 4; off > 0; off >>= 1)
+    if (off < G && q + off < G) addm |= off;
+  const int leader = grp * G;
 
-  for (;;) {
+  // prefetched state of the NEXT segment of this warp: owner-row element and boundary
+  int sg = seg_lo + warp;
+  double own_pref = 0.0;
+  int bend_pref = 0;
+  if (sg < seg_hi) {
+    if (lane < NA) own_pref = __ldg(own_run + (size_t)sg * NAp + lane);
+    if (lane <= R) bend_pref = __ldg(A.seg + (size_t)sg * R + lane);
+  }
+
+  // gathered rows; never-loaded or stale entries are finite and always multiplied by zero
+  double4_t x[UN][CH];
+#pragma unroll
+  for (int un = 0; un < UN; ++un)
+#pragma unroll
+    for (int c = 0; c < CH; ++c) x[un][c] = double4_t{0.0, 0.0, 0.0, 0.0};
+
+  while (sg < seg_hi) {
+    // ---- owner row, group boundaries (first 32 entries were prefetched) ----
+    if (lane < NAp) own_s[lane] = own_pref;
+    if (lane <= R) bend[lane] = bend_pref;
+    for (int a = lane + 32; a < NAp; a += 32)
+      own_s[a] = (a < NA) ? __ldg(own_run + (size_t)sg * NAp + a) : 0.0;
+    for (int r = lane + 32; r <= R; r += 32) bend[r] = __ldg(A.seg + (size_t)sg * R + r);
+    // claim the next segment and start fetching its row now
     int t = 0;
     if (lane == 0) t = atomicAdd(ctr, 1);
-    t = __shfl_sync(kFull, t, 0);
-    const int sg = seg_lo + t;
-    if (sg >= seg_hi) break;
-
-    // ---- owner row, group boundaries ----
-    const double* orow = own_run + (size_t)sg * NAp;
-    for (int a = lane; a < NAp; a += 32) own_s[a] = (a < NA) ? __ldg(orow + a) : 0.0;
-    for (int r = lane; r <= R; r += 32) bend[r] = __ldg(A.seg + (size_t)sg * R + r);
-    __syncwarp();
-
-    // ---- w[r][b] = sum_a own[a] P[a][r][b]: a lane owns output pairs, 128-bit reads ----
-    for (int o2 = lane; o2 < (RNB >> 1); o2 += 32) {
-      double2 acc = make_double2(0.0, 0.0);
-      const double* pcol = Ps + 2 * o2;
-      int a = 0;
-      for (; a + 1 < NA; a += 2) {
-        const double2 ow = *reinterpret_cast<const double2*>(own_s + a);
-        const double2 p0 = *reinterpret_cast<const double2*>(pcol + a * APs);
-        const double2 p1 = *reinterpret_cast<const double2*>(pcol + (a + 1) * APs);
-        acc.x = fma(ow.x, p0.x, acc.x); acc.y = fma(ow.x, p0.y, acc.y);
-        acc.x = fma(ow.y, p1.x, acc.x); acc.y = fma(ow.y, p1.y, acc.y);
-      }
-      if (a < NA) {
-        const double ow = own_s[a];
-        const double2 p0 = *reinterpret_cast<const double2*>(pcol + a * APs);
-        acc.x = fma(ow, p0.x, acc.x); acc.y = fma(ow, p0.y, acc.y);
-      }
-      *reinterpret_cast<double2*>(wg + 2 * o2) = acc;
+    const int sg_next = seg_lo + __shfl_sync(kFull, t, 0);
+    own_pref = 0.0;
+    if (sg_next < seg_hi) {
+      if (lane < NA) own_pref = __ldg(own_run + (size_t)sg_next * NAp + lane);
+      if (lane <= R) bend_pref = __ldg(A.seg + (size_t)sg_next * R + lane);
     }
     __syncwarp();
 
     const int beg = bend[0], end = bend[R];
-    int r_mine = 0, cur_r = 0, next_bound = bend[1];
-    double4_t g[CH], wr[CH];
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      g[c] = double4_t{0.0, 0.0, 0.0, 0.0};
-      wr[c] = lds32(wg + coff[c]);
+    // first chunk's neighbour ids: issue before the w computation to hide their latency
+    int cur_ids = 0;
+    if (lane < SLOTS && beg + lane < end) cur_ids = ld_stream(A.adj + beg + lane);
+
+    // ---- w[r][b] = sum_a own[a] P[a][r][b]: a lane owns output pairs, 128-bit reads ----
+    for (int o2 = lane; o2 < (RNB >> 1); o2 += 32) {
+      double2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
+      const double* pcol = Ps + 2 * o2;
+      int a = 0;
+#pragma unroll 2
+      for (; a + 1 < NA; a += 2) {
+        const double2 ow = *reinterpret_cast<const double2*>(own_s + a);
+        const double2 p0 = *reinterpret_cast<const double2*>(pcol + a * APs);
+        const double2 p1 = *reinterpret_cast<const double2*>(pcol + (a + 1) * APs);
+        acc0.x = fma(ow.x, p0.x, acc0.x); acc0.y = fma(ow.x, p0.y, acc0.y);
+        acc1.x = fma(ow.y, p1.x, acc1.x); acc1.y = fma(ow.y, p1.y, acc1.y);
+      }
+      if (a < NA) {
+        const double ow = own_s[a];
+        const double2 p0 = *reinterpret_cast<const double2*>(pcol + a * APs);
+        acc0.x = fma(ow, p0.x, acc0.x); acc0.y = fma(ow, p0.y, acc0.y);
+      }
+      *reinterpret_cast<double2*>(wg + 2 * o2) = make_double2(acc0.x + acc1.x, acc0.y + acc1.y);
     }
+    __syncwarp();
+
+    int cur_r = 0;
+    double4_t g[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) g[c] = double4_t{0.0, 0.0, 0.0, 0.0};
 
     auto flush = [&](int r) {
 #pragma unroll
@@ -207,72 +245,73 @@ segment_pass_kernel(const SegArgs A) {
       }
     };
 
-    for (int base = beg; base < end; base += UN * RPS) {
-      int my_id = 0;
-      if (lane < UN * RPS && base + lane < end) my_id = ld_stream(A.adj + base + lane);
-      double4_t x[UN][CH];
+    for (int base = beg; base < end; base += SLOTS) {
+      // ---- gather: one 256-bit load per (step, chunk); rows past the end are skipped ----
 #pragma unroll
       for (int un = 0; un < UN; ++un) {
         const int slot = un * RPS + grp;
-        const bool valid = base + slot < end;
-        const int id = __shfl_sync(kFull, my_id, slot & 31);
+        const bool valid = lane_on && (base + slot < end);
+        const int id = __shfl_sync(kFull, cur_ids, slot & 31);
         const double* row = nbr_run + (size_t)id * NBp;
 #pragma unroll
-        for (int c = 0; c < CH; ++c)
-          x[un][c] = (valid && con[c]) ? ldg256(row + coff[c]) : double4_t{0.0, 0.0, 0.0, 0.0};
+        for (int c = 0; c < CH; ++c) ldg256_if(x[un][c], row + coff[c], valid && con[c]);
       }
+      // next chunk's ids (independent of the row loads above)
+      {
+        const int nxt = base + SLOTS + lane;
+        cur_ids = (lane < SLOTS && nxt < end) ? ld_stream(A.adj + nxt) : 0;
+      }
+      // ---- rating level of every slot, lanes <-> slots (rows are sorted by level) ----
+      int r_slot = 0;
+      {
+        const int j = base + lane;
+        for (int r = 1; r < R; ++r) r_slot += (j >= bend[r]);
+      }
+      const int nvalid = min(SLOTS, end - base);
+      const int r_first = __shfl_sync(kFull, r_slot, 0);
+      const int r_last = __shfl_sync(kFull, r_slot, nvalid - 1);
+
+      // ---- per step: S = <w_r, row>, 1/max(S, eps); straight-line so the UN chains overlap ----
+      double inv[UN];
+      int r_un[UN];
 #pragma unroll
       for (int un = 0; un < UN; ++un) {
-        if (base + un * RPS >= end) break;  // warp-uniform
-        const int j = base + un * RPS + grp;
-        const bool valid = lane_on && (j < end);
-        if (valid && j >= next_bound) {     // rating level of this lane's row changes (rare)
-          do { ++r_mine; next_bound = bend[r_mine + 1]; } while (j >= next_bound);
-#pragma unroll
-          for (int c = 0; c < CH; ++c) wr[c] = lds32(wg + r_mine * NBp + coff[c]);
-        }
+        const int slot = un * RPS + grp;
+        r_un[un] = __shfl_sync(kFull, r_slot, slot & 31);
         double part = 0.0;
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
-          part = fma(x[un][c].x, wr[c].x, part);
-          part = fma(x[un][c].y, wr[c].y, part);
-          part = fma(x[un][c].z, wr[c].z, part);
-          part = fma(x[un][c].w, wr[c].w, part);
+          double4_t w = lds32(wg + r_un[un] * NBp + coff[c]);
+          if (!con[c]) w = double4_t{0.0, 0.0, 0.0, 0.0};
+          part = fma(x[un][c].x, w.x, part);
+          part = fma(x[un][c].y, w.y, part);
+          part = fma(x[un][c].z, w.z, part);
+          part = fma(x[un][c].w, w.w, part);
         }
+        double tp = __shfl_down_sync(kFull, part, 4);
+        if (addm & 4) part += tp;
+        tp = __shfl_down_sync(kFull, part, 2);
+        if (addm & 2) part += tp;
+        tp = __shfl_down_sync(kFull, part, 1);
+        if (addm & 1) part += tp;
+        const double tot = __shfl_sync(kFull, part, leader);
+        const bool valid = lane_on && (base + slot < end);
+        inv[un] = valid ? fast_rcp(fmax(tot, kEps)) : 0.0;
+      }
+
+      // ---- g_r += row / S, level by level (usually one level per chunk) ----
+      for (int r = r_first;; ++r) {
+        while (cur_r < r) { flush(cur_r); ++cur_r; }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          if (off < G) {
-            const double tp = __shfl_down_sync(kFull, part, off);
-            if (q + off < G) part += tp;
-          }
-        }
-        const double tot = __shfl_sync(kFull, part, grp * G);
-        // rows past the end carry x = 0, so their (finite) 1/eps never contributes
-        const double inv = fast_rcp(fmax(tot, kEps));
-        if (__all_sync(kFull, !valid || r_mine == cur_r)) {
-#pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            g[c].x = fma(x[un][c].x, inv, g[c].x); g[c].y = fma(x[un][c].y, inv, g[c].y);
-            g[c].z = fma(x[un][c].z, inv, g[c].z); g[c].w = fma(x[un][c].w, inv, g[c].w);
-          }
-        } else {                            // a level boundary falls inside this step
-          double im = (valid && r_mine == cur_r) ? inv : 0.0;
+        for (int un = 0; un < UN; ++un) {
+          const double im = (r_un[un] == r) ? inv[un] : 0.0;
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
             g[c].x = fma(x[un][c].x, im, g[c].x); g[c].y = fma(x[un][c].y, im, g[c].y);
             g[c].z = fma(x[un][c].z, im, g[c].z); g[c].w = fma(x[un][c].w, im, g[c].w);
           }
-          while (__any_sync(kFull, valid && r_mine > cur_r)) {
-            flush(cur_r);
-            ++cur_r;
-            im = (valid && r_mine == cur_r) ? inv : 0.0;
-#pragma unroll
-            for (int c = 0; c < CH; ++c) {
-              g[c].x = x[un][c].x * im; g[c].y = x[un][c].y * im;
-              g[c].z = x[un][c].z * im; g[c].w = x[un][c].w * im;
-            }
-          }
         }
+        if (r >= r_last) break;
       }
     }
     while (cur_r < R) { flush(cur_r); ++cur_r; }
@@ -286,14 +325,17 @@ segment_pass_kernel(const SegArgs A) {
       double acc = 0.0;
       if (a < NA) {
         const double* prow = Ps + a * APs;
-        double acc2 = 0.0;
-        for (int o = 0; o < RNB; o += 2) {
-          const double2 p = *reinterpret_cast<const double2*>(prow + o);
-          const double2 gv = *reinterpret_cast<const double2*>(wg + o);
-          acc = fma(p.x, gv.x, acc);
-          acc2 = fma(p.y, gv.y, acc2);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 2
+        for (int o = 0; o < RNB; o += 4) {     // RNB is a multiple of 4
+          const double2 p0 = *reinterpret_cast<const double2*>(prow + o);
+          const double2 p1 = *reinterpret_cast<const double2*>(prow + o + 2);
+          const double2 g0 = *reinterpret_cast<const double2*>(wg + o);
+          const double2 g1 = *reinterpret_cast<const double2*>(wg + o + 2);
+          a0 = fma(p0.x, g0.x, a0); a1 = fma(p0.y, g0.y, a1);
+          a2 = fma(p1.x, g1.x, a2); a3 = fma(p1.y, g1.y, a3);
         }
-        acc = (acc + acc2) * own_s[a];
+        acc = ((a0 + a1) + (a2 + a3)) * own_s[a];
         if (A.normalize) acc = acc / scale;
       }
       orow_out[a] = acc;
@@ -303,6 +345,7 @@ segment_pass_kernel(const SegArgs A) {
       for (int o = lane; o < RNB; o += 32) gdst[o] = wg[o];
     }
     __syncwarp();
+    sg = sg_next;
   }
 }
 
@@ -437,7 +480,7 @@ static PassShape choose_shape(int NBp) {
   if ((CHenv == 1 || CHenv == 2 || CHenv == 4 || CHenv == 8) && (NCH + CHenv - 1) / CHenv <= 32) CH = CHenv;
   int G = (NCH + CH - 1) / CH;
   int Genv = env_int("MMSBM_G", 0);
-  if (Genv >= G && Genv <= 32) G = Genv;
+  if (Genv >= G && Genv <= 8) G = Genv;      // the group reduction has 3 shuffle levels
   int RPS = 32 / G;
   int UN = CH >= 4 ? 1 : 4 / CH;
   while (UN > 1 && UN * RPS > 32) UN >>= 1;
