@@ -51,7 +51,7 @@ extern "C" {
 #define MMSBM_ABI_VERSION 1
 
 #define MMSBM_EINVAL  (-1)   /* bad argument (null pointer, size out of range)      */
-#define MMSBM_ERANGE  (-2)   /* shape not supported (K or L > 256, id*R overflows)   */
+#define MMSBM_ERANGE  (-2)   /* shape not supported (K or L > 256, R > 31, id*R >= 2^31) */
 #define MMSBM_ENOMEM  (-3)   /* workspace too small                                  */
 #define MMSBM_ENODEV  (-4)   /* no usable CUDA device (there is no CPU fallback)     */
 
@@ -90,8 +90,9 @@ int mmsbm_em_step(const int32_t* useg_dev, const int32_t* uadj_dev, const int32_
                   const double* theta_dev, const double* eta_dev, const double* pr_dev,
                   double* theta_out_dev, double* eta_out_dev, double* pr_out_dev,
                   int32_t flags, void* workspace_dev, size_t workspace_bytes, void* stream);
-/* the same step with CUDA events around its four launches (measurement only: it waits for
- * the stream); ms4 = device ms of {by-user pass, by-item pass, pr accumulate, pr finalize} */
+/* the same step with CUDA events between its stages (measurement only: it waits for the
+ * stream); ms6 = device ms of {P tables + w GEMMs, by-user pass, by-item pass, n GEMMs,
+ * pr accumulate, pr finalize} */
 int mmsbm_em_step_profiled(const int32_t* useg_dev, const int32_t* uadj_dev, const int32_t* udeg_dev,
                            const int32_t* iseg_dev, const int32_t* iadj_dev, const int32_t* ideg_dev,
                            int64_t n_ratings, int32_t n_users, int32_t n_items, int32_t n_levels,
@@ -99,7 +100,7 @@ int mmsbm_em_step_profiled(const int32_t* useg_dev, const int32_t* uadj_dev, con
                            const double* theta_dev, const double* eta_dev, const double* pr_dev,
                            double* theta_out_dev, double* eta_out_dev, double* pr_out_dev,
                            int32_t flags, void* workspace_dev, size_t workspace_bytes, void* stream,
-                           float* ms4);
+                           float* ms6);
 /* ``iterations`` steps ping-ponging between (theta,eta,pr)_a and _b, no host sync;
  * the result is in the _a buffers when iterations is even, else in _b.
  * Replaces the loop src/mmsbm.py:243-250. */
