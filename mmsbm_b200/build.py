@@ -10,7 +10,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmmsbm_b200.so")
-SOURCES = ["em_step.cu", "graph_build.cu", "reductions.cu", "host_api.cu"]
+SOURCES = ["em_step.cu", "seg_inst_ch1.cu", "seg_inst_ch2.cu", "seg_inst_ch4.cu", "graph_build.cu",
+           "reductions.cu", "host_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall", "-DMMSBM_B200",   # no --use_fast_math: IEEE fp64 throughout
@@ -34,7 +35,7 @@ def _stale(target, deps):
 def build_library(force=False, verbose=False):
     """Compile every .cu to an object (in parallel) and link the shared library."""
     nvcc = _nvcc()
-    headers = [os.path.join(CSRC, "common.cuh"),
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "segment_pass.cuh"),
                os.path.join(HERE, "..", "include", "mmsbm_b200.h"), os.path.abspath(__file__)]
     objs, jobs = [], []
     for src in SOURCES:

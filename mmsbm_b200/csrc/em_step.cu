@@ -31,53 +31,16 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "segment_pass.cuh"
 
 namespace mmsbm {
 
-constexpr int kWarps = 8;       // warps per CTA of the segment pass
 constexpr int kPrSlabs = 64;
 constexpr int kPrThreads = 256;
 constexpr int kPrAcc = 8;       // accumulators per thread per output tile
 constexpr int kPrBatch = 16;    // segments staged per smem batch
 constexpr int kGemmThreads = 256;
 constexpr int kGemmBK = 32;     // k-slab of the small GEMM (even)
-
-struct alignas(16) double4_t { double x, y, z, w; };
-
-// predicated 256-bit read-only load (LDG.E.ENL2.256 on sm_100a): a lane's 32-byte chunk of a
-// row; the registers keep their (finite) previous contents when !pred
-__device__ __forceinline__ void ldg256_if(double4_t& v, const double* p, bool pred) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
-      "@p ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];\n\t}"
-      : "+d"(v.x), "+d"(v.y), "+d"(v.z), "+d"(v.w) : "l"(p), "r"((int)pred));
-}
-__device__ __forceinline__ void stg256(double* p, const double4_t& v) {
-  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w)
-               : "memory");
-}
-__device__ __forceinline__ double4_t lds32(const double* p) {   // two 128-bit shared loads
-  const double2 a = *reinterpret_cast<const double2*>(p);
-  const double2 b = *reinterpret_cast<const double2*>(p + 2);
-  return double4_t{a.x, a.y, b.x, b.y};
-}
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
-                   (uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// 1/x for x in [eps, huge): MUFU.RCP64H seed (~2^-20) + two Newton steps -> <= ~1 ulp
-__device__ __forceinline__ double fast_rcp(double x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  return fma(r, e, r);
-}
 
 // ---- P in operand layout -------------------------------------------------------------------
 // For a side with owner dim NA (stride lda), neighbour dim NB (stride NBp), RNB = R*NBp and
@@ -177,206 +140,6 @@ __global__ void __launch_bounds__(kGemmThreads) small_gemm_kernel(const GemmArgs
     }
     stg256(g.C + off, v);
   }
-}
-
-// ---- the segment pass ------------------------------------------------------------------------
-struct SegArgs {
-  const int32_t* seg;   // [nseg*R+1]
-  const int32_t* adj;   // [N] neighbour ids, grouped by (segment, level)
-  const double* nbr;    // [S][nnbr][NBp]
-  double* wg;           // [S][nseg][R*NBp]  in: w   out: g (in place)
-  int nseg, nnbr, NBp, R, G, RPS, segs_per_cta;
-};
-
-inline size_t seg_smem_bytes(const SegArgs& a) {
-  return (size_t)kWarps * 2 * a.R * a.NBp * 8 + 32;
-}
-
-template <int CH, int UN>
-__global__ void __launch_bounds__(kWarps * 32, 2)
-segment_pass_kernel(const SegArgs A) {
-  extern __shared__ __align__(32) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int run = blockIdx.y;
-  const int R = A.R, NBp = A.NBp, RNB = R * NBp;
-  const int NCH = NBp >> 2;                      // 32-byte chunks per neighbour row
-  const int G = A.G, RPS = A.RPS;
-  const int SLOTS = UN * RPS;                    // ratings per chunk of work (<= 32)
-
-  double* wbuf = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 2 * RNB;   // [2][RNB]
-  int* ctr = reinterpret_cast<int*>(smem_raw + (size_t)kWarps * 2 * RNB * 8);
-  if (threadIdx.x == 0) *ctr = kWarps;           // warps start on segments 0..kWarps-1
-  __syncthreads();
-
-  const int grp = lane / G, q = lane - grp * G;
-  const bool lane_on = grp < RPS;
-  const int seg_lo = blockIdx.x * A.segs_per_cta;
-  const int seg_hi = min(seg_lo + A.segs_per_cta, A.nseg);
-  const double* nbr_run = A.nbr + (size_t)run * A.nnbr * NBp;
-  double* wg_run = A.wg + (size_t)run * A.nseg * RNB;
-  // lane-constant chunk offsets (in doubles), validity, and the add mask of the 3-level
-  // shuffle reduction over a group (G <= 8): bit `off` set iff lane q adds lane q+off
-  int coff[CH];
-  bool con[CH];
-#pragma unroll
-  for (int c = 0; c < CH; ++c) {
-    const int chunk = c * G + q;
-    con[c] = lane_on && chunk < NCH;
-    coff[c] = con[c] ? 4 * chunk : 0;
-  }
-  int addm = 0;
-#pragma unroll
-  for (int off = 4; off > 0; off >>= 1)
-    if (off < G && q + off < G) addm |= off;
-  const int leader = grp * G;
-
-  // w row of a segment -> shared memory, asynchronously (16-byte pieces)
-  auto fetch_w = [&](int s_, int b_) {
-    const double* src = wg_run + (size_t)s_ * RNB;
-    double* dst = wbuf + (size_t)b_ * RNB;
-    for (int p = lane; p < (RNB >> 1); p += 32) cp_async16(dst + 2 * p, src + 2 * p);
-  };
-
-  int sg = seg_lo + warp, buf = 0;
-  int bend_pref = 0;                             // lane r <= R holds the start of level r
-  if (sg < seg_hi) {
-    if (lane <= R) bend_pref = __ldg(A.seg + (size_t)sg * R + lane);
-    fetch_w(sg, 0);
-  }
-  cp_async_commit();
-
-  // gathered rows; never-loaded or stale entries are finite and always multiplied by zero
-  double4_t x[UN][CH];
-#pragma unroll
-  for (int un = 0; un < UN; ++un)
-#pragma unroll
-    for (int c = 0; c < CH; ++c) x[un][c] = double4_t{0.0, 0.0, 0.0, 0.0};
-
-  while (sg < seg_hi) {
-    const int bend_reg = bend_pref;
-    // claim the next segment, start fetching its boundaries and its w row
-    int t = 0;
-    if (lane == 0) t = atomicAdd(ctr, 1);
-    const int sg_next = seg_lo + __shfl_sync(kFull, t, 0);
-    if (sg_next < seg_hi) {
-      if (lane <= R) bend_pref = __ldg(A.seg + (size_t)sg_next * R + lane);
-      fetch_w(sg_next, buf ^ 1);
-    }
-    cp_async_commit();
-    const int beg = __shfl_sync(kFull, bend_reg, 0), end = __shfl_sync(kFull, bend_reg, R);
-    int cur_ids = 0;
-    if (lane < SLOTS && beg + lane < end) cur_ids = ld_stream(A.adj + beg + lane);
-    cp_async_wait<1>();                          // this segment's w has landed
-    __syncwarp();
-    const double* wb = wbuf + (size_t)buf * RNB;
-    double* gout = wg_run + (size_t)sg * RNB;
-
-    int cur_r = 0, w_lvl = -1;
-    double4_t g[CH], wr[CH];
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      g[c] = double4_t{0.0, 0.0, 0.0, 0.0};
-      wr[c] = double4_t{0.0, 0.0, 0.0, 0.0};
-    }
-
-    auto flush = [&](int r) {                    // g_r: sum over the groups, then to global
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        double4_t v = g[c];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          if (off < RPS) {
-            const double tx = __shfl_down_sync(kFull, v.x, off * G);
-            const double ty = __shfl_down_sync(kFull, v.y, off * G);
-            const double tz = __shfl_down_sync(kFull, v.z, off * G);
-            const double tw = __shfl_down_sync(kFull, v.w, off * G);
-            if (grp + off < RPS) { v.x += tx; v.y += ty; v.z += tz; v.w += tw; }
-          }
-        }
-        if (grp == 0 && con[c]) stg256(gout + r * NBp + coff[c], v);
-        g[c] = double4_t{0.0, 0.0, 0.0, 0.0};
-      }
-    };
-
-    for (int base = beg; base < end; base += SLOTS) {
-      // ---- gather: one 256-bit load per (step, chunk); rows past the end are skipped ----
-#pragma unroll
-      for (int un = 0; un < UN; ++un) {
-        const int slot = un * RPS + grp;
-        const bool valid = lane_on && (base + slot < end);
-        const int id = __shfl_sync(kFull, cur_ids, slot & 31);
-        const double* row = nbr_run + (size_t)id * NBp;
-#pragma unroll
-        for (int c = 0; c < CH; ++c) ldg256_if(x[un][c], row + coff[c], valid && con[c]);
-      }
-      // next chunk's ids (independent of the row loads above)
-      {
-        const int nxt = base + SLOTS + lane;
-        cur_ids = (lane < SLOTS && nxt < end) ? ld_stream(A.adj + nxt) : 0;
-      }
-      // ---- rating level of every slot, lanes <-> slots (rows are sorted by level) ----
-      int r_slot = 0;
-      {
-        const int j = base + lane;
-        for (int r = 1; r < R; ++r) r_slot += (j >= __shfl_sync(kFull, bend_reg, r));
-      }
-      const int nvalid = min(SLOTS, end - base);
-      const int r_first = __shfl_sync(kFull, r_slot, 0);
-      const int r_last = __shfl_sync(kFull, r_slot, nvalid - 1);
-
-      // ---- per step: S = <w_r, row>, 1/max(S, eps) ----
-      double inv[UN];
-      int r_un[UN];
-#pragma unroll
-      for (int un = 0; un < UN; ++un) {
-        const int slot = un * RPS + grp;
-        r_un[un] = __shfl_sync(kFull, r_slot, slot & 31);
-        if (r_un[un] != w_lvl) {                 // level change: reload this lane's w chunks
-          w_lvl = r_un[un];
-#pragma unroll
-          for (int c = 0; c < CH; ++c)
-            if (con[c]) wr[c] = lds32(wb + w_lvl * NBp + coff[c]);
-        }
-        double part = 0.0;
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          part = fma(x[un][c].x, wr[c].x, part);
-          part = fma(x[un][c].y, wr[c].y, part);
-          part = fma(x[un][c].z, wr[c].z, part);
-          part = fma(x[un][c].w, wr[c].w, part);
-        }
-        double tp = __shfl_down_sync(kFull, part, 4);
-        if (addm & 4) part += tp;
-        tp = __shfl_down_sync(kFull, part, 2);
-        if (addm & 2) part += tp;
-        tp = __shfl_down_sync(kFull, part, 1);
-        if (addm & 1) part += tp;
-        const double tot = __shfl_sync(kFull, part, leader);
-        const bool valid = lane_on && (base + slot < end);
-        inv[un] = valid ? fast_rcp(fmax(tot, kEps)) : 0.0;
-      }
-
-      // ---- g_r += row / S, level by level (usually one level per chunk) ----
-      for (int r = r_first;; ++r) {
-        while (cur_r < r) { flush(cur_r); ++cur_r; }
-#pragma unroll
-        for (int un = 0; un < UN; ++un) {
-          const double im = (r_un[un] == r) ? inv[un] : 0.0;
-#pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            g[c].x = fma(x[un][c].x, im, g[c].x); g[c].y = fma(x[un][c].y, im, g[c].y);
-            g[c].z = fma(x[un][c].z, im, g[c].z); g[c].w = fma(x[un][c].w, im, g[c].w);
-          }
-        }
-        if (r >= r_last) break;
-      }
-    }
-    while (cur_r < R) { flush(cur_r); ++cur_r; }
-    __syncwarp();
-    buf ^= 1;
-    sg = sg_next;
-  }
-  cp_async_wait<0>();
 }
 
 // ---- n_pr: Acc[a][r][b] = sum_seg own[seg][a] g[seg][r][b], per-CTA private accumulators,
@@ -491,65 +254,66 @@ __global__ void finalize_pr_kernel(double* pr, int KL_total, int R) {
 }
 
 // ------------------------------------------------------------------------------------------
-struct PassShape { int CH, UN, G, RPS; };
+struct PassShape { int G, CH, UN, MINB; };
 
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
 }
 
+// NCH 32-byte chunks per row are spread over G lanes x CH chunks per lane with G <= 8 (three
+// shuffle levels per rating at most); UN steps in flight; MINB CTAs per SM the kernel is
+// compiled for.  Defaults from the sweep in profiles/ (more resident warps beat deeper unroll).
 static PassShape choose_shape(int NBp) {
-  // NCH 32-byte chunks per row are spread over G lanes x CH chunks per lane; G <= 8 keeps the
-  // per-rating shuffle reduction at 3 levels.  UN steps (RPS ratings each) are in flight.
   const int NCH = NBp / 4;
   int CH = 8;
   for (int c = 1; c <= 8; c *= 2) {
     if ((NCH + c - 1) / c <= 8) { CH = c; break; }
   }
-  int CHenv = env_int("MMSBM_CH", 0);
-  if ((CHenv == 1 || CHenv == 2 || CHenv == 4 || CHenv == 8) && (NCH + CHenv - 1) / CHenv <= 8) CH = CHenv;
-  int G = (NCH + CH - 1) / CH;
-  int Genv = env_int("MMSBM_G", 0);
-  if (Genv >= G && Genv <= 8) G = Genv;      // the group reduction has 3 shuffle levels
-  int RPS = 32 / G;
-  int UN = CH >= 4 ? 1 : 4 / CH;
-  while (UN > 1 && UN * RPS > 32) UN >>= 1;
-  int UNenv = env_int("MMSBM_UN", 0);
-  if ((UNenv == 1 || UNenv == 2 || UNenv == 4) && UNenv * CH <= 4 && UNenv * RPS <= 32) UN = UNenv;
-  return PassShape{CH, UN, G, RPS};
+  const int G = (NCH + CH - 1) / CH;
+  PassShape sh{G, CH, 1, 1};
+  if (CH == 1) { sh.UN = (G == 1) ? 1 : 2; sh.MINB = 3; }
+  else if (CH == 2) { sh.UN = 1; sh.MINB = 3; }
+  return sh;
 }
 
 static int segs_per_cta_for(int nseg) {
-  // aim at >= 8 waves of 2 CTAs/SM on 148 SMs, at least one segment per warp
-  int spc = nseg / (148 * 2 * 8);
-  if (spc < kWarps) spc = kWarps;
+  // dynamic scheduling inside a CTA needs several segments per warp to balance; keep >= ~600
+  // CTAs per run so that the grid still covers 148 SMs x 3 several times over
+  int spc = nseg / 592;
+  if (spc < 2 * kWarps) spc = 2 * kWarps;
   if (spc > 64) spc = 64;
-  return env_int("MMSBM_SPC", spc);
+  const int e = env_int("MMSBM_SPC", 0);
+  return e > 0 ? e : spc;
 }
 
 static int launch_segment_pass(SegArgs a, int n_runs, cudaStream_t st) {
-  const PassShape sh = choose_shape(a.NBp);
-  a.G = sh.G; a.RPS = sh.RPS;
+  PassShape sh = choose_shape(a.NBp);
   a.segs_per_cta = segs_per_cta_for(a.nseg);
-  dim3 grid((a.nseg + a.segs_per_cta - 1) / a.segs_per_cta, n_runs);
-  dim3 block(kWarps * 32);
-  size_t smem = seg_smem_bytes(a);
+  const dim3 grid((a.nseg + a.segs_per_cta - 1) / a.segs_per_cta, n_runs);
+  const size_t smem = seg_smem_bytes(a);
   MMSBM_REQUIRE(smem <= 227 * 1024, MMSBM_ERANGE,
                 "segment pass needs %zu bytes of shared memory (R=%d, row stride %d)", smem, a.R, a.NBp);
-#define MMSBM_SEG_CASE(CHv, UNv)                                                              \
-  if (sh.CH == CHv && sh.UN == UNv) {                                                         \
-    auto kern = segment_pass_kernel<CHv, UNv>;                                                \
-    MMSBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, block, smem, st>>>(a);                                                       \
-    MMSBM_LAUNCH_CHECK("segment_pass_kernel");                                                \
-    return 0;                                                                                 \
+  auto go = [&](const PassShape& p) {
+    switch (p.CH) {
+      case 1: return launch_segment_pass_ch1(a, p.G, p.UN, p.MINB, grid, smem, st);
+      case 2: return launch_segment_pass_ch2(a, p.G, p.UN, p.MINB, grid, smem, st);
+      case 4: return launch_segment_pass_ch4(a, p.G, p.UN, p.MINB, grid, smem, st);
+      default: return launch_segment_pass_ch8(a, p.G, p.UN, p.MINB, grid, smem, st);
+    }
+  };
+  // tuning overrides (only combinations that were instantiated take effect)
+  const int un_e = env_int("MMSBM_UN", 0), occ_e = env_int("MMSBM_OCC", 0);
+  if (un_e > 0 || occ_e > 0) {
+    PassShape alt = sh;
+    if (un_e > 0) alt.UN = un_e;
+    if (occ_e > 0) alt.MINB = occ_e;
+    const int rc = go(alt);
+    if (rc != MMSBM_ERANGE) return rc;
   }
-  MMSBM_SEG_CASE(1, 1) MMSBM_SEG_CASE(1, 2) MMSBM_SEG_CASE(1, 4)
-  MMSBM_SEG_CASE(2, 1) MMSBM_SEG_CASE(2, 2)
-  MMSBM_SEG_CASE(4, 1) MMSBM_SEG_CASE(8, 1)
-#undef MMSBM_SEG_CASE
-  set_error("no segment-pass variant for CH=%d UN=%d", sh.CH, sh.UN);
-  return MMSBM_ERANGE;
+  const int rc = go(sh);
+  if (rc == MMSBM_ERANGE) set_error("no segment-pass variant for G=%d CH=%d UN=%d", sh.G, sh.CH, sh.UN);
+  return rc;
 }
 
 template <bool EPI>
@@ -647,13 +411,13 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
   MMSBM_MARK(1);
   // ---- by-user pass: g of every user (gathers eta rows) ----
   {
-    SegArgs a{useg, uadj, eta, wg_u, U, I, d.ldl, R, 0, 0, 0};
+    SegArgs a{useg, uadj, eta, wg_u, U, I, d.ldl, R, 0};
     if ((rc = launch_segment_pass(a, S, st))) return rc;
   }
   MMSBM_MARK(2);
   // ---- by-item pass: g of every item (gathers theta rows) ----
   {
-    SegArgs a{iseg, iadj, theta, wg_i, I, U, d.ldk, R, 0, 0, 0};
+    SegArgs a{iseg, iadj, theta, wg_i, I, U, d.ldk, R, 0};
     if ((rc = launch_segment_pass(a, S, st))) return rc;
   }
   MMSBM_MARK(3);

@@ -1,0 +1,326 @@
+// The hot kernel of the EM iteration: one warp per segment (a user in the by-user pass, an
+// item in the by-item pass) streams the segment's ratings.  See em_step.cu for the algebra.
+//
+// Lane mapping (all compile time): groups of G lanes own one rating each, RPS = 32/G ratings
+// per step, UN steps in flight (SLOTS = UN*RPS ratings per chunk of work).  Lane q of a group
+// holds CH 32-byte chunks of the gathered neighbour row (chunk c*G+q), fetched with ONE 256-bit
+// read-only load per chunk (LDG.E.ENL2.256) -- a group covers a whole row in one instruction,
+// so the L1 sees ~1.6 wavefronts per rating instead of 10 for a lane-per-row layout
+// (profiles/r1_gather_microbench_*.txt).
+//
+//   S_n   = <w_level, row>      4*CH DFMA per lane + an all-reduce over the G lanes
+//   1/S_n                       MUFU.RCP64H + two Newton steps
+//   g    += row / S_n           4*CH DFMA per lane, registers
+//   g_level -> global           once per (segment, level): sum over the RPS groups by shuffles
+//
+// w comes from the W table (small_gemm_kernel) through cp.async, prefetched one segment ahead
+// into a double-buffered shared-memory row; g overwrites W in place.  Ratings are stored
+// grouped by level, so a chunk sees one level except where a boundary falls inside it; that
+// case re-runs the chunk once per level present with the other levels weighted zero.
+#pragma once
+#include "common.cuh"
+
+namespace mmsbm {
+
+constexpr int kWarps = 8;       // warps per CTA of the segment pass
+
+struct alignas(16) double4_t { double x, y, z, w; };
+
+// 256-bit read-only load (LDG.E.ENL2.256 on sm_100a): a lane's 32-byte chunk of a row
+__device__ __forceinline__ double4_t ldg256(const double* p) {
+  double4_t v;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg256(double* p, const double4_t& v) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ double4_t lds32(const double* p) {   // two 128-bit shared loads
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  const double2 b = *reinterpret_cast<const double2*>(p + 2);
+  return double4_t{a.x, a.y, b.x, b.y};
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// 1/max(x, eps) for x >= 0: MUFU.RCP64H seed (~2^-20) + two Newton steps -> <= ~1 ulp
+__device__ __forceinline__ double rcp_clamped(double x) {
+  x = (x < kEps) ? kEps : x;
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
+struct SegArgs {
+  const int32_t* seg;   // [nseg*R+1]
+  const int32_t* adj;   // [N] neighbour ids, grouped by (segment, level)
+  const double* nbr;    // [S][nnbr][NBp]
+  double* wg;           // [S][nseg][R*NBp]  in: w   out: g (in place)
+  int nseg, nnbr, NBp, R, segs_per_cta;
+};
+
+inline size_t seg_smem_bytes(const SegArgs& a) {
+  return (size_t)kWarps * 2 * a.R * a.NBp * 8 + 32;
+}
+
+// Sum of `part` over the G consecutive lanes of a group, delivered to every lane of the group.
+// Power-of-two groups are aligned, so xor shuffles do; otherwise windows of 1, 2, 4 lanes are
+// accumulated by rotating inside the group (source lanes (q+1)%G, (q+2)%G, ... of the group).
+// Lanes of one group may round differently in the last bit; each stays deterministic.
+template <int G>
+struct GroupSum {
+  int s1, s2, s4, s6;
+  __device__ __forceinline__ GroupSum(int leader, int q) {
+    s1 = (leader + (q + 1) % G) & 31;
+    s2 = (leader + (q + 2) % G) & 31;
+    s4 = (leader + (q + 4) % G) & 31;
+    s6 = (leader + (q + 6) % G) & 31;
+  }
+  __device__ __forceinline__ double operator()(double p) const {
+    if constexpr (G == 1) {
+      return p;
+    } else if constexpr (G == 2) {
+      return p + __shfl_xor_sync(kFull, p, 1);
+    } else if constexpr (G == 4) {
+      p += __shfl_xor_sync(kFull, p, 1);
+      return p + __shfl_xor_sync(kFull, p, 2);
+    } else if constexpr (G == 8) {
+      p += __shfl_xor_sync(kFull, p, 1);
+      p += __shfl_xor_sync(kFull, p, 2);
+      return p + __shfl_xor_sync(kFull, p, 4);
+    } else if constexpr (G == 3) {
+      const double w2 = p + __shfl_sync(kFull, p, s1);          // lanes q, q+1
+      return w2 + __shfl_sync(kFull, p, s2);                    // + q+2
+    } else if constexpr (G == 5) {
+      const double w2 = p + __shfl_sync(kFull, p, s1);          // q, q+1
+      const double w4 = w2 + __shfl_sync(kFull, w2, s2);        // q .. q+3
+      return w4 + __shfl_sync(kFull, p, s4);                    // + q+4
+    } else if constexpr (G == 6) {
+      const double w2 = p + __shfl_sync(kFull, p, s1);
+      const double w4 = w2 + __shfl_sync(kFull, w2, s2);
+      return w4 + __shfl_sync(kFull, w2, s4);                   // + (q+4, q+5)
+    } else {
+      static_assert(G == 7, "groups have 1..8 lanes");
+      const double w2 = p + __shfl_sync(kFull, p, s1);
+      const double w4 = w2 + __shfl_sync(kFull, w2, s2);
+      const double w6 = w4 + __shfl_sync(kFull, w2, s4);        // q .. q+5
+      return w6 + __shfl_sync(kFull, p, s6);                    // + q+6
+    }
+  }
+};
+
+template <int G, int CH, int UN, int MINB>
+__global__ void __launch_bounds__(kWarps * 32, MINB)
+segment_pass_kernel(const SegArgs A) {
+  constexpr int RPS = 32 / G;                    // ratings per step
+  constexpr int SLOTS = UN * RPS;                // ratings per chunk of work (<= 32)
+  static_assert(SLOTS <= 32, "a chunk's ids must fit one coalesced 32-lane load");
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int run = blockIdx.y;
+  const int R = A.R, NBp = A.NBp, RNB = R * NBp;
+  const int NCH = NBp >> 2;                      // 32-byte chunks per neighbour row
+
+  double* wbuf = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 2 * RNB;   // [2][RNB]
+  int* ctr = reinterpret_cast<int*>(smem_raw + (size_t)kWarps * 2 * RNB * 8);
+  if (threadIdx.x == 0) *ctr = kWarps;           // warps start on segments 0..kWarps-1
+  __syncthreads();
+
+  const int grp = lane / G, q = lane - grp * G;
+  const bool lane_on = grp < RPS;                // lanes past RPS*G idle (32 % G of them)
+  const int seg_lo = blockIdx.x * A.segs_per_cta;
+  const int seg_hi = min(seg_lo + A.segs_per_cta, A.nseg);
+  const double* nbr_run = A.nbr + (size_t)run * A.nnbr * NBp;
+  double* wg_run = A.wg + (size_t)run * A.nseg * RNB;
+  int coff[CH];                                  // lane-constant chunk offsets (in doubles)
+  bool con[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int chunk = c * G + q;
+    con[c] = lane_on && chunk < NCH;
+    coff[c] = con[c] ? 4 * chunk : 0;            // idle lanes re-read chunk 0 (same line)
+  }
+  const GroupSum<G> group_sum(grp * G, q);
+
+  // w row of a segment -> shared memory, asynchronously (16-byte pieces)
+  auto fetch_w = [&](int s_, int b_) {
+    const double* src = wg_run + (size_t)s_ * RNB;
+    double* dst = wbuf + (size_t)b_ * RNB;
+    for (int p = lane; p < (RNB >> 1); p += 32) cp_async16(dst + 2 * p, src + 2 * p);
+  };
+
+  int sg = seg_lo + warp, buf = 0;
+  int bend_pref = 0;                             // lane r <= R holds the start of level r
+  if (sg < seg_hi) {
+    if (lane <= R) bend_pref = __ldg(A.seg + (size_t)sg * R + lane);
+    fetch_w(sg, 0);
+  }
+  cp_async_commit();
+
+  while (sg < seg_hi) {
+    const int bend_reg = bend_pref;
+    // claim the next segment, start fetching its boundaries and its w row
+    int t = 0;
+    if (lane == 0) t = atomicAdd(ctr, 1);
+    const int sg_next = seg_lo + __shfl_sync(kFull, t, 0);
+    if (sg_next < seg_hi) {
+      if (lane <= R) bend_pref = __ldg(A.seg + (size_t)sg_next * R + lane);
+      fetch_w(sg_next, buf ^ 1);
+    }
+    cp_async_commit();
+    const int beg = __shfl_sync(kFull, bend_reg, 0), end = __shfl_sync(kFull, bend_reg, R);
+    // ids of the first chunk; slots past the end read row 0 (in bounds, weight zero)
+    int cur_ids = 0;
+    if (lane < SLOTS && beg + lane < end) cur_ids = ld_stream(A.adj + beg + lane);
+    cp_async_wait<1>();                          // this segment's w has landed
+    __syncwarp();
+    const double* wb = wbuf + (size_t)buf * RNB;
+    double* gout = wg_run + (size_t)sg * RNB;
+
+    int cur_r = 0;                               // level the accumulators g belong to
+    int lvl = 0, nb = __shfl_sync(kFull, bend_reg, 1);   // level of the chunk's first row, its end
+    int w_lvl = -1;                              // level whose w chunks sit in wr (warp-uniform)
+    double4_t g[CH], wr[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      g[c] = double4_t{0.0, 0.0, 0.0, 0.0};
+      wr[c] = double4_t{0.0, 0.0, 0.0, 0.0};
+    }
+
+    auto flush = [&](int r) {                    // g_r: sum over the groups, then to global
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        double4_t v = g[c];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          if (off < RPS) {
+            const double tx = __shfl_down_sync(kFull, v.x, off * G);
+            const double ty = __shfl_down_sync(kFull, v.y, off * G);
+            const double tz = __shfl_down_sync(kFull, v.z, off * G);
+            const double tw = __shfl_down_sync(kFull, v.w, off * G);
+            if (grp + off < RPS) { v.x += tx; v.y += ty; v.z += tz; v.w += tw; }
+          }
+        }
+        if (grp == 0 && con[c]) stg256(gout + r * NBp + coff[c], v);
+        g[c] = double4_t{0.0, 0.0, 0.0, 0.0};
+      }
+    };
+    auto load_w = [&](int r) {                   // this lane's chunks of w_r (warp-uniform r)
+      if (w_lvl != r) {
+        w_lvl = r;
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+          if (con[c]) wr[c] = lds32(wb + r * NBp + coff[c]);
+      }
+    };
+
+    for (int base = beg; base < end; base += SLOTS) {
+      // ---- gather: one 256-bit load per (step, chunk) ----
+      double4_t x[UN][CH];
+#pragma unroll
+      for (int un = 0; un < UN; ++un) {
+        const int id = __shfl_sync(kFull, cur_ids, (un * RPS + grp) & 31);
+        const double* row = nbr_run + (size_t)id * NBp;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) x[un][c] = ldg256(row + coff[c]);
+      }
+      // next chunk's ids (independent of the row loads above)
+      {
+        const int nxt = base + SLOTS + lane;
+        cur_ids = (lane < SLOTS && nxt < end) ? ld_stream(A.adj + nxt) : 0;
+      }
+      // ---- levels present in this chunk (rows are sorted by level; all warp-uniform) ----
+      while (base >= nb) { ++lvl; nb = __shfl_sync(kFull, bend_reg, lvl + 1); }
+      const int last = min(base + SLOTS, end) - 1;
+
+      if (last < nb && last - base == SLOTS - 1) {
+        // ---- fast path: a full chunk of one level ----
+        while (cur_r < lvl) { flush(cur_r); ++cur_r; }
+        load_w(lvl);
+#pragma unroll
+        for (int un = 0; un < UN; ++un) {
+          double part = 0.0;
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            part = fma(x[un][c].x, wr[c].x, part); part = fma(x[un][c].y, wr[c].y, part);
+            part = fma(x[un][c].z, wr[c].z, part); part = fma(x[un][c].w, wr[c].w, part);
+          }
+          const double im = rcp_clamped(group_sum(part));
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            g[c].x = fma(x[un][c].x, im, g[c].x); g[c].y = fma(x[un][c].y, im, g[c].y);
+            g[c].z = fma(x[un][c].z, im, g[c].z); g[c].w = fma(x[un][c].w, im, g[c].w);
+          }
+        }
+      } else {
+        // ---- general path: ragged tail and/or level boundaries inside the chunk ----
+        int r_slot = 0;                          // level of slot `lane`
+        {
+          const int j = base + lane;
+          for (int r = 1; r < R; ++r) r_slot += (j >= __shfl_sync(kFull, bend_reg, r));
+        }
+        const int r_last = __shfl_sync(kFull, r_slot, last - base);
+        int r_mine[UN];
+#pragma unroll
+        for (int un = 0; un < UN; ++un) {
+          const int slot = un * RPS + grp;
+          r_mine[un] = __shfl_sync(kFull, r_slot, slot & 31);
+          if (!lane_on || base + slot > last) r_mine[un] = -1;      // never matches a level
+        }
+        for (int r = lvl;; ++r) {
+          while (cur_r < r) { flush(cur_r); ++cur_r; }
+          load_w(r);
+#pragma unroll
+          for (int un = 0; un < UN; ++un) {
+            double part = 0.0;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+              part = fma(x[un][c].x, wr[c].x, part); part = fma(x[un][c].y, wr[c].y, part);
+              part = fma(x[un][c].z, wr[c].z, part); part = fma(x[un][c].w, wr[c].w, part);
+            }
+            const double rc = rcp_clamped(group_sum(part));
+            const double im = (r_mine[un] == r) ? rc : 0.0;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+              g[c].x = fma(x[un][c].x, im, g[c].x); g[c].y = fma(x[un][c].y, im, g[c].y);
+              g[c].z = fma(x[un][c].z, im, g[c].z); g[c].w = fma(x[un][c].w, im, g[c].w);
+            }
+          }
+          if (r >= r_last) break;
+        }
+      }
+    }
+    while (cur_r < R) { flush(cur_r); ++cur_r; }
+    __syncwarp();
+    buf ^= 1;
+    sg = sg_next;
+  }
+  cp_async_wait<0>();
+}
+
+// one instantiation unit per CH (seg_inst_ch*.cu) keeps compile time parallel
+int launch_segment_pass_ch1(const SegArgs& a, int G, int UN, int MINB, dim3 grid, size_t smem, cudaStream_t st);
+int launch_segment_pass_ch2(const SegArgs& a, int G, int UN, int MINB, dim3 grid, size_t smem, cudaStream_t st);
+int launch_segment_pass_ch4(const SegArgs& a, int G, int UN, int MINB, dim3 grid, size_t smem, cudaStream_t st);
+int launch_segment_pass_ch8(const SegArgs& a, int G, int UN, int MINB, dim3 grid, size_t smem, cudaStream_t st);
+
+#define MMSBM_SEG_LAUNCH(Gv, CHv, UNv, MBv)                                                    \
+  if (G == Gv && UN == UNv && MINB == MBv) {                                                   \
+    auto kern = segment_pass_kernel<Gv, CHv, UNv, MBv>;                                        \
+    MMSBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, dim3(kWarps * 32), smem, st>>>(a);                                            \
+    MMSBM_LAUNCH_CHECK("segment_pass_kernel");                                                 \
+    return 0;                                                                                  \
+  }
+
+}  // namespace mmsbm
