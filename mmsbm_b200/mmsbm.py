@@ -22,7 +22,7 @@ from .engine import Engine, predict_stats
 from .expectation_maximization import ExpectationMaximization
 from .helpers import get_n_per_group, structure_folds
 from .logger import setup_logger
-from .parallel import dist_info, gather_runs, shard_runs
+from .parallel import RatingShardedEngine, dist_info, gather_runs, shard_runs
 
 
 class MMSBM:
@@ -42,6 +42,10 @@ class MMSBM:
         Log the likelihood every 50 iterations.
     backend : str, default="auto"
         "auto" or "b200".  There is no CPU backend.
+    shard : str, default="runs"  (extension; only matters under torch.distributed)
+        "runs": independent runs round-robin over ranks, no per-iteration communication.
+        "ratings": every run is split by user range over all ranks, with an all-reduce of the
+        eta / pr accumulators per iteration (for one run too large or too slow for one GPU).
     """
 
     data_handler = None
@@ -55,7 +59,7 @@ class MMSBM:
     rng = None
 
     def __init__(self, user_groups, item_groups, iterations=400, sampling=1, seed=None,
-                 debug=False, backend="auto"):
+                 debug=False, backend="auto", shard="runs"):
         self.start_time = datetime.now()
         self.user_groups = user_groups
         self.item_groups = item_groups
@@ -63,6 +67,8 @@ class MMSBM:
         self.sampling = sampling
         self.debug = debug
         self.backend = backend
+        assert shard in ("runs", "ratings"), "shard must be 'runs' or 'ratings'"
+        self.shard = shard
 
         self.rng = np.random.default_rng(seed)
         self.child_states = self.rng.bit_generator._seed_seq.spawn(sampling)
@@ -170,6 +176,13 @@ class MMSBM:
         train = self.data_handler.format_train_data(data)
         self._prepare_objects(train)
         rank, world = dist_info()
+        if world > 1 and self.shard == "ratings":
+            eng = RatingShardedEngine(train, self.p + 1, self.m + 1, self._dims['n_ratings'],
+                                      self.user_groups, self.item_groups)
+            every = list(range(self.sampling))
+            done = self._run_batch(eng, [self.child_states[i] for i in every], every)
+            self.results = [done[i] for i in every]
+            return
         mine = shard_runs(self.sampling, rank, world)
         local = self._run_batch(self._engine, [self.child_states[i] for i in mine], mine) if mine else {}
         self.results = gather_runs(local, self.sampling)

@@ -68,3 +68,69 @@ def allreduce_sum_(tensors):
         n = t.numel()
         t.copy_(flat[off:off + n].view_as(t))
         off += n
+
+
+def shard_rows_by_user(data, n_users, rank, world):
+    """Rows of this rank when ratings are sharded by contiguous user range balanced by rating
+    count.  Returns (local rows with user ids shifted to start at 0, lo, hi, bounds)."""
+    data = np.asarray(data)
+    deg = np.bincount(data[:, 0], minlength=n_users)
+    bounds = user_partition(deg, world)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    keep = (data[:, 0] >= lo) & (data[:, 0] < hi)
+    local = data[keep].copy()
+    local[:, 0] -= lo
+    return local, lo, hi, bounds
+
+
+class RatingShardedEngine:
+    """S runs with the ratings sharded by user range over the ranks of the default process
+    group (the Netflix-shaped config).  Rank g owns theta[lo_g:hi_g] and
+    all ratings of those users; eta and pr are replicated.  One exchange per iteration: the
+    unnormalised n_eta and n_pr are summed over ranks (NCCL all-reduce over NVLink), then every
+    rank applies the same normalisation epilogue (mmsbm_em_finalize)."""
+
+    def __init__(self, data, n_users, n_items, n_levels, K, L, device=None):
+        from . import _lib
+        from .engine import Engine
+        self._lib = _lib
+        self.rank, self.world = dist_info()
+        if self.world > n_users:
+            raise ValueError("more ranks than users")
+        self.U = int(n_users)
+        local, self.lo, self.hi, self.bounds = shard_rows_by_user(data, n_users, self.rank, self.world)
+        self.engine = Engine(local, self.hi - self.lo, n_items, n_levels, K, L, device=device)
+        self.N = int(np.asarray(data).shape[0])
+        # the degree that normalises eta is the GLOBAL item degree
+        self.ideg = self.engine.ideg.clone()
+        if self.world > 1:
+            dist.all_reduce(self.ideg, op=dist.ReduceOp.SUM)
+
+    def set_params(self, theta, eta, pr):
+        theta = np.asarray(theta)
+        if theta.ndim == 2:
+            theta, eta, pr = theta[None], np.asarray(eta)[None], np.asarray(pr)[None]
+        self.engine.set_params(theta[:, self.lo:self.hi], eta, pr)
+
+    def run(self, iterations):
+        e = self.engine
+        for _ in range(int(iterations)):
+            _, eta_raw, pr_raw = e.step_raw(self._lib.RAW_ETA_PR)   # theta' is final: users are owned
+            allreduce_sum_([eta_raw, pr_raw])
+            e.finalize(eta_raw, pr_raw, ideg=self.ideg)
+            e.swap()
+
+    def likelihood(self):
+        lik = self.engine.likelihood_device().clone()
+        if self.world > 1:
+            dist.all_reduce(lik, op=dist.ReduceOp.SUM)
+        return lik.cpu().numpy()
+
+    def get_params(self):
+        """Full (theta [S,U,K], eta, pr) on every rank."""
+        th, et, pr = self.engine.get_params()
+        if self.world == 1:
+            return th, et, pr
+        parts = [None] * self.world
+        dist.all_gather_object(parts, th)
+        return np.concatenate(parts, axis=1), et, pr
