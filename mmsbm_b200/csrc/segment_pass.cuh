@@ -16,7 +16,7 @@
 // w comes from the W table (small_gemm_kernel) through cp.async, prefetched one segment ahead
 // into a double-buffered shared-memory row; g overwrites W in place.  Ratings are stored
 // grouped by level, so a chunk sees one level except where a boundary falls inside it; that
-// case re-runs the chunk once per level present with the other levels weighted zero.
+// case reads w per row and repeats only the accumulation once per level present.
 #pragma once
 #include "common.cuh"
 
@@ -264,6 +264,8 @@ segment_pass_kernel(const SegArgs A) {
         }
       } else {
         // ---- general path: ragged tail and/or level boundaries inside the chunk ----
+        // every row takes the w of ITS level (per-lane shared-memory read), the E-step runs
+        // once; only the accumulation is repeated per level present, other levels weigh zero
         int r_slot = 0;                          // level of slot `lane`
         {
           const int j = base + lane;
@@ -271,25 +273,29 @@ segment_pass_kernel(const SegArgs A) {
         }
         const int r_last = __shfl_sync(kFull, r_slot, last - base);
         int r_mine[UN];
+        double rc[UN];
 #pragma unroll
         for (int un = 0; un < UN; ++un) {
           const int slot = un * RPS + grp;
-          r_mine[un] = __shfl_sync(kFull, r_slot, slot & 31);
-          if (!lane_on || base + slot > last) r_mine[un] = -1;      // never matches a level
+          const int rs = __shfl_sync(kFull, r_slot, slot & 31);
+          double part = 0.0;
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            if (con[c]) {
+              const double4_t w = lds32(wb + rs * NBp + coff[c]);
+              part = fma(x[un][c].x, w.x, part); part = fma(x[un][c].y, w.y, part);
+              part = fma(x[un][c].z, w.z, part); part = fma(x[un][c].w, w.w, part);
+            }
+          }
+          rc[un] = rcp_clamped(group_sum(part));
+          r_mine[un] = (lane_on && base + slot <= last) ? rs : -1;   // -1 never matches a level
         }
+        w_lvl = -1;                              // wr no longer describes a single level
         for (int r = lvl;; ++r) {
           while (cur_r < r) { flush(cur_r); ++cur_r; }
-          load_w(r);
 #pragma unroll
           for (int un = 0; un < UN; ++un) {
-            double part = 0.0;
-#pragma unroll
-            for (int c = 0; c < CH; ++c) {
-              part = fma(x[un][c].x, wr[c].x, part); part = fma(x[un][c].y, wr[c].y, part);
-              part = fma(x[un][c].z, wr[c].z, part); part = fma(x[un][c].w, wr[c].w, part);
-            }
-            const double rc = rcp_clamped(group_sum(part));
-            const double im = (r_mine[un] == r) ? rc : 0.0;
+            const double im = (r_mine[un] == r) ? rc[un] : 0.0;
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
               g[c].x = fma(x[un][c].x, im, g[c].x); g[c].y = fma(x[un][c].y, im, g[c].y);
