@@ -41,6 +41,7 @@ constexpr int kPrAcc = 8;       // accumulators per thread per output tile
 constexpr int kPrBatch = 16;    // segments staged per smem batch
 constexpr int kGemmThreads = 256;
 constexpr int kGemmBK = 32;     // k-slab of the small GEMM (even)
+constexpr int kGemmTR = 4;      // rows per thread tile of the small GEMM
 
 // ---- P in operand layout -------------------------------------------------------------------
 // For a side with owner dim NA (stride lda), neighbour dim NB (stride NBp), RNB = R*NBp and
@@ -64,8 +65,8 @@ __global__ void prep_p_kernel(const double* pr, int K, int L, int R, int ldk, in
 }
 
 // ---- C[M x N] = A[M x Kd] . B[Kd x N] for tall-skinny fp64 problems (N, Kd <= ~1k) ------------
-// One 4x4 output tile per thread, rg row groups x N/4 column groups per CTA, k in slabs of
-// kGemmBK staged in shared memory.  EPI: C = C o own / max(deg,1).  fp64 FMA pipe, no tensor
+// Persistent CTAs: B is staged in shared memory once, then each CTA walks row tiles; one 4x4
+// output tile per thread (rg row groups x N/4 column groups), A in k-slabs of kGemmBK.  EPI: C = C o own / max(deg,1).  fp64 FMA pipe, no tensor
 // cores (B200 DMMA is no faster than the vector pipe and the path is not GEMM-bound).
 struct GemmArgs {
   const double* A;      // [S][M][lda]
@@ -78,67 +79,174 @@ struct GemmArgs {
 
 template <bool EPI>
 __global__ void __launch_bounds__(kGemmThreads) small_gemm_kernel(const GemmArgs g) {
+  constexpr int TR = kGemmTR;                  // rows of the register tile (columns: 4)
   extern __shared__ __align__(32) unsigned char smem_raw[];
-  const int BM = 4 * g.rg, AS = kGemmBK + 2;
-  double* As = reinterpret_cast<double*>(smem_raw);          // [BM][AS]
-  double* Bs = As + (size_t)BM * AS;                         // [kGemmBK][N]
-  const int run = blockIdx.y, row0 = blockIdx.x * BM;
-  const int ncg = g.N >> 2;
+  const int BM = TR * g.rg, AS = kGemmBK + 2;
+  double* Bs = reinterpret_cast<double*>(smem_raw);          // [Kd][N]   whole B, staged once
+  double* As = Bs + (size_t)g.Kd * g.N;                      // [BM][AS]  one k-slab of a row tile
+  const int run = blockIdx.y;
+  const int ncg = g.N >> 2, half = g.N >> 1;
   const int rgid = threadIdx.x / ncg, cg = threadIdx.x - rgid * ncg;
   const bool active = rgid < g.rg;
   const double* A = g.A + (size_t)run * g.M * g.lda;
-  const double* B = g.B + (size_t)run * g.Kd * g.N;
-  double acc[4][4];
+  {
+    const double2* B2 = reinterpret_cast<const double2*>(g.B + (size_t)run * g.Kd * g.N);
+    double2* Bs2 = reinterpret_cast<double2*>(Bs);
+    for (int t = threadIdx.x; t < (g.Kd * g.N) >> 1; t += kGemmThreads) Bs2[t] = __ldg(B2 + t);
+  }
+  const int n_tiles = (g.M + BM - 1) / BM;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int row0 = tile * BM;
+    double acc[TR][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TR; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
-  for (int k0 = 0; k0 < g.Kd; k0 += kGemmBK) {
-    const int bk = min(kGemmBK, g.Kd - k0);            // even: Kd is a multiple of 4
-    __syncthreads();
-    for (int t = threadIdx.x; t < BM * bk; t += kGemmThreads) {
-      const int m = t / bk, kk = t - m * bk;
-      As[m * AS + kk] = (row0 + m < g.M) ? __ldg(A + (size_t)(row0 + m) * g.lda + k0 + kk) : 0.0;
-    }
-    for (int t = threadIdx.x; t < bk * g.N; t += kGemmThreads) Bs[t] = __ldg(B + (size_t)k0 * g.N + t);
-    __syncthreads();
-    if (active) {
-      const double* ap = As + (size_t)(4 * rgid) * AS;
-      const double* bp = Bs + 4 * cg;
-      for (int kk = 0; kk < bk; kk += 2) {
-        double2 a[4];
+    for (int k0 = 0; k0 < g.Kd; k0 += kGemmBK) {
+      const int bk = min(kGemmBK, g.Kd - k0);          // multiple of 4
+      const int bk2 = bk >> 1;
+      __syncthreads();
+      for (int t = threadIdx.x; t < BM * bk2; t += kGemmThreads) {   // 128-bit staging of the A slab
+        const int m = t / bk2, p2 = t - m * bk2;
+        double2 v = make_double2(0.0, 0.0);
+        if (row0 + m < g.M) v = __ldg(reinterpret_cast<const double2*>(A + (size_t)(row0 + m) * g.lda + k0) + p2);
+        *reinterpret_cast<double2*>(As + m * AS + 2 * p2) = v;
+      }
+      __syncthreads();
+      if (active) {
+        // thread tile: rows TR*rgid.., columns {2cg, 2cg+1, N/2+2cg, N/2+2cg+1}: consecutive
+        // threads read consecutive 16-byte pieces of a B row (no bank conflicts); the A reads of
+        // a warp are (nearly) uniform, i.e. broadcasts
+        const double* ap = As + (size_t)(TR * rgid) * AS;
+        const double* bp = Bs + (size_t)k0 * g.N + 2 * cg;
+        for (int kk = 0; kk < bk; kk += 2) {
+          const double2 b00 = *reinterpret_cast<const double2*>(bp + (size_t)kk * g.N);
+          const double2 b01 = *reinterpret_cast<const double2*>(bp + (size_t)kk * g.N + half);
+          const double2 b10 = *reinterpret_cast<const double2*>(bp + (size_t)(kk + 1) * g.N);
+          const double2 b11 = *reinterpret_cast<const double2*>(bp + (size_t)(kk + 1) * g.N + half);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const double2*>(ap + i * AS + kk);
-        const double4_t b0 = lds32(bp + (size_t)kk * g.N);
-        const double4_t b1 = lds32(bp + (size_t)(kk + 1) * g.N);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          acc[i][0] = fma(a[i].x, b0.x, acc[i][0]); acc[i][1] = fma(a[i].x, b0.y, acc[i][1]);
-          acc[i][2] = fma(a[i].x, b0.z, acc[i][2]); acc[i][3] = fma(a[i].x, b0.w, acc[i][3]);
-          acc[i][0] = fma(a[i].y, b1.x, acc[i][0]); acc[i][1] = fma(a[i].y, b1.y, acc[i][1]);
-          acc[i][2] = fma(a[i].y, b1.z, acc[i][2]); acc[i][3] = fma(a[i].y, b1.w, acc[i][3]);
+          for (int i = 0; i < TR; ++i) {
+            const double2 a = *reinterpret_cast<const double2*>(ap + i * AS + kk);
+            acc[i][0] = fma(a.x, b00.x, acc[i][0]); acc[i][1] = fma(a.x, b00.y, acc[i][1]);
+            acc[i][2] = fma(a.x, b01.x, acc[i][2]); acc[i][3] = fma(a.x, b01.y, acc[i][3]);
+            acc[i][0] = fma(a.y, b10.x, acc[i][0]); acc[i][1] = fma(a.y, b10.y, acc[i][1]);
+            acc[i][2] = fma(a.y, b11.x, acc[i][2]); acc[i][3] = fma(a.y, b11.y, acc[i][3]);
+          }
         }
       }
     }
-  }
-  if (!active) return;
+    if (active) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = row0 + 4 * rgid + i;
-    if (m >= g.M) continue;
-    const size_t off = ((size_t)run * g.M + m) * g.N + 4 * cg;
-    double4_t v{acc[i][0], acc[i][1], acc[i][2], acc[i][3]};
-    if (EPI) {
-      const double2 o0 = __ldg(reinterpret_cast<const double2*>(g.own + off));
-      const double2 o1 = __ldg(reinterpret_cast<const double2*>(g.own + off + 2));
-      v.x *= o0.x; v.y *= o0.y; v.z *= o1.x; v.w *= o1.y;
-      if (g.normalize) {
-        const double d = (double)max(__ldg(g.deg + m), 1);
-        v.x = v.x / d; v.y = v.y / d; v.z = v.z / d; v.w = v.w / d;
+      for (int i = 0; i < TR; ++i) {
+        const int m = row0 + TR * rgid + i;
+        if (m >= g.M) continue;
+        const size_t off = ((size_t)run * g.M + m) * g.N + 2 * cg;
+        double2 v0 = make_double2(acc[i][0], acc[i][1]), v1 = make_double2(acc[i][2], acc[i][3]);
+        if (EPI) {
+          const double2 o0 = __ldg(reinterpret_cast<const double2*>(g.own + off));
+          const double2 o1 = __ldg(reinterpret_cast<const double2*>(g.own + off + half));
+          v0.x *= o0.x; v0.y *= o0.y; v1.x *= o1.x; v1.y *= o1.y;
+          if (g.normalize) {
+            const double d = (double)max(__ldg(g.deg + m), 1);
+            v0.x = v0.x / d; v0.y = v0.y / d; v1.x = v1.x / d; v1.y = v1.y / d;
+          }
+        }
+        *reinterpret_cast<double2*>(g.C + off) = v0;
+        *reinterpret_cast<double2*>(g.C + off + half) = v1;
       }
     }
-    stg256(g.C + off, v);
+  }
+}
+
+// ---- lane-per-row variants of the two contractions (row strides <= 32 doubles) ---------------
+// A lane owns one segment: its own-row (w) or its accumulators (n) live in registers, the P
+// table sits in shared memory and every read of it is a warp-wide broadcast (one wavefront),
+// so the kernels need no barriers and little LSU bandwidth; HBM traffic is the W / G rows.
+constexpr int kRowThreads = 256;
+
+template <int LD>
+__global__ void __launch_bounds__(kRowThreads) row_w_kernel(const double* __restrict__ own,
+                                                            const double* __restrict__ pw,
+                                                            double* __restrict__ W, int M, int RNB) {
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  double* Ps = reinterpret_cast<double*>(smem_raw);          // [LD][RNB]
+  const int run = blockIdx.y;
+  {
+    const double2* src = reinterpret_cast<const double2*>(pw + (size_t)run * LD * RNB);
+    double2* dst = reinterpret_cast<double2*>(Ps);
+    for (int t = threadIdx.x; t < (LD * RNB) >> 1; t += kRowThreads) dst[t] = __ldg(src + t);
+  }
+  __syncthreads();
+  const double* own_run = own + (size_t)run * M * LD;
+  double* w_run = W + (size_t)run * M * RNB;
+  for (int m = blockIdx.x * kRowThreads + threadIdx.x; m < M; m += gridDim.x * kRowThreads) {
+    double o[LD];
+#pragma unroll
+    for (int c = 0; c < LD / 4; ++c) {
+      const double4_t v = ldg256(own_run + (size_t)m * LD + 4 * c);
+      o[4 * c] = v.x; o[4 * c + 1] = v.y; o[4 * c + 2] = v.z; o[4 * c + 3] = v.w;
+    }
+    double* wrow = w_run + (size_t)m * RNB;
+    for (int ob = 0; ob < RNB; ob += 4) {
+      double4_t acc{0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int a = 0; a < LD; ++a) {
+        const double4_t p = lds32(Ps + a * RNB + ob);
+        acc.x = fma(o[a], p.x, acc.x); acc.y = fma(o[a], p.y, acc.y);
+        acc.z = fma(o[a], p.z, acc.z); acc.w = fma(o[a], p.w, acc.w);
+      }
+      stg256(wrow + ob, acc);
+    }
+  }
+}
+
+template <int LD>
+__global__ void __launch_bounds__(kRowThreads) row_n_kernel(const double* __restrict__ G,
+                                                            const double* __restrict__ pn,
+                                                            const double* __restrict__ own,
+                                                            const int32_t* __restrict__ deg,
+                                                            double* __restrict__ out, int M, int RNB,
+                                                            int normalize) {
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  double* Ps = reinterpret_cast<double*>(smem_raw);          // [RNB][LD]
+  const int run = blockIdx.y;
+  {
+    const double2* src = reinterpret_cast<const double2*>(pn + (size_t)run * LD * RNB);
+    double2* dst = reinterpret_cast<double2*>(Ps);
+    for (int t = threadIdx.x; t < (LD * RNB) >> 1; t += kRowThreads) dst[t] = __ldg(src + t);
+  }
+  __syncthreads();
+  const double* g_run = G + (size_t)run * M * RNB;
+  const double* own_run = own + (size_t)run * M * LD;
+  double* out_run = out + (size_t)run * M * LD;
+  for (int m = blockIdx.x * kRowThreads + threadIdx.x; m < M; m += gridDim.x * kRowThreads) {
+    double acc[LD];
+#pragma unroll
+    for (int a = 0; a < LD; ++a) acc[a] = 0.0;
+    const double* grow = g_run + (size_t)m * RNB;
+    for (int ob = 0; ob < RNB; ob += 4) {
+      const double4_t gq = ldg256(grow + ob);
+      const double gv[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int c = 0; c < LD / 4; ++c) {
+          const double4_t p = lds32(Ps + (ob + j) * LD + 4 * c);
+          acc[4 * c] = fma(gv[j], p.x, acc[4 * c]);         acc[4 * c + 1] = fma(gv[j], p.y, acc[4 * c + 1]);
+          acc[4 * c + 2] = fma(gv[j], p.z, acc[4 * c + 2]); acc[4 * c + 3] = fma(gv[j], p.w, acc[4 * c + 3]);
+        }
+      }
+    }
+    double d = 1.0;
+    if (normalize) d = (double)max(__ldg(deg + m), 1);
+#pragma unroll
+    for (int c = 0; c < LD / 4; ++c) {
+      const double4_t ov = ldg256(own_run + (size_t)m * LD + 4 * c);
+      double4_t v{acc[4 * c] * ov.x, acc[4 * c + 1] * ov.y, acc[4 * c + 2] * ov.z, acc[4 * c + 3] * ov.w};
+      if (normalize) { v.x = v.x / d; v.y = v.y / d; v.z = v.z / d; v.w = v.w / d; }
+      stg256(out_run + (size_t)m * LD + 4 * c, v);
+    }
   }
 }
 
@@ -324,14 +432,56 @@ static int launch_gemm(GemmArgs g, int n_runs, cudaStream_t st) {
   int rg = kGemmThreads / ncg;
   if (rg > 32) rg = 32;
   g.rg = rg;
-  const int BM = 4 * rg;
-  size_t smem = ((size_t)BM * (kGemmBK + 2) + (size_t)kGemmBK * g.N) * 8;
-  MMSBM_REQUIRE(smem <= 227 * 1024, MMSBM_ERANGE, "small gemm needs %zu bytes of shared memory", smem);
+  const int BM = kGemmTR * rg;
+  size_t smem = ((size_t)g.Kd * g.N + (size_t)BM * (kGemmBK + 2)) * 8;
+  MMSBM_REQUIRE(smem <= 227 * 1024, MMSBM_ERANGE,
+                "small gemm needs %zu bytes of shared memory (K*L*R too large)", smem);
   auto kern = small_gemm_kernel<EPI>;
   MMSBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<dim3((g.M + BM - 1) / BM, n_runs), kGemmThreads, smem, st>>>(g);
+  const int n_tiles = (g.M + BM - 1) / BM;
+  int per_run = (148 * 3 + n_runs - 1) / n_runs;      // ~3 persistent CTAs per SM in total
+  if (per_run > n_tiles) per_run = n_tiles;
+  if (per_run < 1) per_run = 1;
+  kern<<<dim3(per_run, n_runs), kGemmThreads, smem, st>>>(g);
   MMSBM_LAUNCH_CHECK("small_gemm_kernel");
   return 0;
+}
+
+// dispatch of the two contractions: lane-per-row kernels for row strides <= 32, tiled GEMM beyond
+static int launch_w(const double* own, const double* pw, double* W, int M, int LD, int RNB, int n_runs,
+                    cudaStream_t st) {
+  const size_t smem = (size_t)LD * RNB * 8;
+  const int gx = min((M + kRowThreads - 1) / kRowThreads, 148 * 2);
+#define MMSBM_ROW_W(LDv)                                                                        \
+  if (LD == LDv && smem <= 200 * 1024) {                                                        \
+    MMSBM_CUDA(cudaFuncSetAttribute(row_w_kernel<LDv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    row_w_kernel<LDv><<<dim3(gx, n_runs), kRowThreads, smem, st>>>(own, pw, W, M, RNB);         \
+    MMSBM_LAUNCH_CHECK("row_w_kernel");                                                         \
+    return 0;                                                                                   \
+  }
+  MMSBM_ROW_W(4) MMSBM_ROW_W(8) MMSBM_ROW_W(12) MMSBM_ROW_W(16) MMSBM_ROW_W(20) MMSBM_ROW_W(24)
+  MMSBM_ROW_W(28) MMSBM_ROW_W(32)
+#undef MMSBM_ROW_W
+  GemmArgs g{own, pw, W, nullptr, nullptr, M, RNB, LD, LD, 0, 0};
+  return launch_gemm<false>(g, n_runs, st);
+}
+
+static int launch_n(const double* G, const double* pn, const double* own, const int32_t* deg, double* out,
+                    int M, int LD, int RNB, int normalize, int n_runs, cudaStream_t st) {
+  const size_t smem = (size_t)LD * RNB * 8;
+  const int gx = min((M + kRowThreads - 1) / kRowThreads, 148 * 2);
+#define MMSBM_ROW_N(LDv)                                                                        \
+  if (LD == LDv && smem <= 200 * 1024) {                                                        \
+    MMSBM_CUDA(cudaFuncSetAttribute(row_n_kernel<LDv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    row_n_kernel<LDv><<<dim3(gx, n_runs), kRowThreads, smem, st>>>(G, pn, own, deg, out, M, RNB, normalize); \
+    MMSBM_LAUNCH_CHECK("row_n_kernel");                                                         \
+    return 0;                                                                                   \
+  }
+  MMSBM_ROW_N(4) MMSBM_ROW_N(8) MMSBM_ROW_N(12) MMSBM_ROW_N(16) MMSBM_ROW_N(20) MMSBM_ROW_N(24)
+  MMSBM_ROW_N(28) MMSBM_ROW_N(32)
+#undef MMSBM_ROW_N
+  GemmArgs g{G, pn, out, own, deg, M, LD, RNB, RNB, 0, normalize};
+  return launch_gemm<true>(g, n_runs, st);
 }
 
 struct EmDims {
@@ -403,10 +553,8 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
     const int total = d.ldk * d.ldl * R;
     prep_p_kernel<<<dim3((total + 255) / 256, S), 256, 0, st>>>(pr, K, L, R, d.ldk, d.ldl, pw_u, pn_u, pw_i, pn_i);
     MMSBM_LAUNCH_CHECK("prep_p_kernel");
-    GemmArgs gu{theta, pw_u, wg_u, nullptr, nullptr, U, d.rnb_u, d.ldk, d.ldk, 0, 0};
-    if ((rc = launch_gemm<false>(gu, S, st))) return rc;
-    GemmArgs gi{eta, pw_i, wg_i, nullptr, nullptr, I, d.rnb_i, d.ldl, d.ldl, 0, 0};
-    if ((rc = launch_gemm<false>(gi, S, st))) return rc;
+    if ((rc = launch_w(theta, pw_u, wg_u, U, d.ldk, d.rnb_u, S, st))) return rc;
+    if ((rc = launch_w(eta, pw_i, wg_i, I, d.ldl, d.rnb_i, S, st))) return rc;
   }
   MMSBM_MARK(1);
   // ---- by-user pass: g of every user (gathers eta rows) ----
@@ -423,12 +571,10 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
   MMSBM_MARK(3);
   // ---- theta' and eta' = (g x Pn) o own / max(deg,1) ----
   {
-    GemmArgs gu{wg_u, pn_u, theta_out, theta, udeg, U, d.ldk, d.rnb_u, d.rnb_u, 0,
-                (flags & MMSBM_RAW_THETA) ? 0 : 1};
-    if ((rc = launch_gemm<true>(gu, S, st))) return rc;
-    GemmArgs gi{wg_i, pn_i, eta_out, eta, ideg, I, d.ldl, d.rnb_i, d.rnb_i, 0,
-                (flags & MMSBM_RAW_ETA_PR) ? 0 : 1};
-    if ((rc = launch_gemm<true>(gi, S, st))) return rc;
+    if ((rc = launch_n(wg_u, pn_u, theta, udeg, theta_out, U, d.ldk, d.rnb_u,
+                       (flags & MMSBM_RAW_THETA) ? 0 : 1, S, st))) return rc;
+    if ((rc = launch_n(wg_i, pn_i, eta, ideg, eta_out, I, d.ldl, d.rnb_i,
+                       (flags & MMSBM_RAW_ETA_PR) ? 0 : 1, S, st))) return rc;
   }
   MMSBM_MARK(4);
   // ---- pr' ----
