@@ -372,7 +372,7 @@ static int env_int(const char* name, int dflt) {
 // NCH 32-byte chunks per row are spread over G lanes x CH chunks per lane with G <= 8 (three
 // shuffle levels per rating at most); UN steps in flight; MINB CTAs per SM the kernel is
 // compiled for.  Defaults from the sweep in profiles/ (more resident warps beat deeper unroll).
-static PassShape choose_shape(int NBp) {
+static PassShape choose_shape(int NBp, double avg_degree) {
   const int NCH = NBp / 4;
   int CH = 8;
   for (int c = 1; c <= 8; c *= 2) {
@@ -381,6 +381,8 @@ static PassShape choose_shape(int NBp) {
   const int G = (NCH + CH - 1) / CH;
   PassShape sh{G, CH, 1, 1};
   if (CH == 1) { sh.UN = (G == 1) ? 1 : 2; sh.MINB = 3; }
+  // short segments are latency bound: one step in flight but 4 CTAs/SM wins there (G = 5 only)
+  if (CH == 1 && G == 5 && avg_degree < 256.0) { sh.UN = 1; sh.MINB = 4; }
   else if (CH == 2) { sh.UN = 1; sh.MINB = 3; }
   return sh;
 }
@@ -395,8 +397,8 @@ static int segs_per_cta_for(int nseg) {
   return e > 0 ? e : spc;
 }
 
-static int launch_segment_pass(SegArgs a, int n_runs, cudaStream_t st) {
-  PassShape sh = choose_shape(a.NBp);
+static int launch_segment_pass(SegArgs a, int64_t n_ratings, int n_runs, cudaStream_t st) {
+  PassShape sh = choose_shape(a.NBp, (double)n_ratings / (double)a.nseg);
   a.segs_per_cta = segs_per_cta_for(a.nseg);
   const dim3 grid((a.nseg + a.segs_per_cta - 1) / a.segs_per_cta, n_runs);
   const size_t smem = seg_smem_bytes(a);
@@ -560,13 +562,13 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
   // ---- by-user pass: g of every user (gathers eta rows) ----
   {
     SegArgs a{useg, uadj, eta, wg_u, U, I, d.ldl, R, 0};
-    if ((rc = launch_segment_pass(a, S, st))) return rc;
+    if ((rc = launch_segment_pass(a, N, S, st))) return rc;
   }
   MMSBM_MARK(2);
   // ---- by-item pass: g of every item (gathers theta rows) ----
   {
     SegArgs a{iseg, iadj, theta, wg_i, I, U, d.ldk, R, 0};
-    if ((rc = launch_segment_pass(a, S, st))) return rc;
+    if ((rc = launch_segment_pass(a, N, S, st))) return rc;
   }
   MMSBM_MARK(3);
   // ---- theta' and eta' = (g x Pn) o own / max(deg,1) ----

@@ -50,15 +50,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// 1/max(x, eps) for x >= 0: MUFU.RCP64H seed (~2^-20) + two Newton steps -> <= ~1 ulp
+// 1/max(x, eps) for x >= 0: MUFU.RCP64H seed r (relative error e ~ 2^-20) refined by one
+// third-order step r(1 + e + e^2), error e^3 ~ 2^-60 -> correctly rounded up to ~1 ulp
 __device__ __forceinline__ double rcp_clamped(double x) {
   x = (x < kEps) ? kEps : x;
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  return fma(r, e, r);
+  const double e = fma(-x, r, 1.0);
+  const double t = fma(e, e, e);
+  return fma(r, t, r);
 }
 
 struct SegArgs {
@@ -249,13 +249,13 @@ segment_pass_kernel(const SegArgs A) {
         load_w(lvl);
 #pragma unroll
         for (int un = 0; un < UN; ++un) {
-          double part = 0.0;
+          double part = 0.0, part2 = 0.0;
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
-            part = fma(x[un][c].x, wr[c].x, part); part = fma(x[un][c].y, wr[c].y, part);
-            part = fma(x[un][c].z, wr[c].z, part); part = fma(x[un][c].w, wr[c].w, part);
+            part = fma(x[un][c].x, wr[c].x, part); part2 = fma(x[un][c].y, wr[c].y, part2);
+            part = fma(x[un][c].z, wr[c].z, part); part2 = fma(x[un][c].w, wr[c].w, part2);
           }
-          const double im = rcp_clamped(group_sum(part));
+          const double im = rcp_clamped(group_sum(part + part2));
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
             g[c].x = fma(x[un][c].x, im, g[c].x); g[c].y = fma(x[un][c].y, im, g[c].y);
