@@ -69,6 +69,13 @@ int         mmsbm_row_stride(int32_t k);
 /* kernels launched by this library on the calling thread since it was loaded */
 int64_t     mmsbm_launch_count(void);
 
+/* ---- a11 -> a8: the reference's encoded int64 [N,3] array (src/data_handler.py:57-61) split into
+ *      int32 columns on the device; *bad_dev is set to 1 when an id is outside [0,U)x[0,I)x[0,R)
+ *      (R <= 0 skips the rating check) ------------------------------------------------------- */
+int mmsbm_split_triples(const int64_t* data_dev, int64_t n_ratings, int32_t n_users, int32_t n_items,
+                        int32_t n_levels, int32_t* user_dev, int32_t* item_dev, int32_t* level_dev,
+                        int32_t* bad_dev, void* stream);
+
 /* ---- a8: index structure, replaces MMSBM._prepare_objects (src/mmsbm.py:93-122) -------- */
 int mmsbm_graph_workspace_bytes(int64_t n_ratings, int32_t n_users, int32_t n_items,
                                 int32_t n_levels, size_t* bytes);

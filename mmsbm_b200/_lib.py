@@ -21,6 +21,7 @@ _PROTOS = {
     "mmsbm_device_count": (C.c_int, []),
     "mmsbm_launch_count": (_i64, []),
     "mmsbm_row_stride": (C.c_int, [_i32]),
+    "mmsbm_split_triples": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mmsbm_graph_workspace_bytes": (C.c_int, [_i64, _i32, _i32, _i32, C.POINTER(_sz)]),
     "mmsbm_graph_build": (C.c_int, [_vp] * 3 + [_i64, _i32, _i32, _i32] + [_vp] * 8 + [_vp, _sz, _vp]),
     "mmsbm_em_workspace_bytes": (C.c_int, [_i32] * 6 + [C.POINTER(_sz)]),

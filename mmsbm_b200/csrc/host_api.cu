@@ -3,8 +3,10 @@
 // this library on a private stream, copy out and synchronise.  No CPU arithmetic happens
 // here: even the int64 -> int32 split and the row padding run on the device.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <vector>
 
 #include "common.cuh"
@@ -45,18 +47,22 @@ __global__ void unpad_rows_kernel(const double* src, double* dst, size_t rows, i
   dst[t] = src[row * ld + c];
 }
 
-// everything one host call allocates; freed on scope exit
+// everything one host call allocates: stream-ordered allocations from the device's default
+// memory pool (kept warm between calls: release threshold = unlimited), freed on scope exit
 struct Scope {
   std::vector<void*> ptrs;
   cudaStream_t st = nullptr;
   ~Scope() {
-    for (void* p : ptrs) cudaFree(p);
-    if (st) cudaStreamDestroy(st);
+    if (st) {
+      for (void* p : ptrs) cudaFreeAsync(p, st);
+      cudaStreamSynchronize(st);
+      cudaStreamDestroy(st);
+    }
   }
   template <typename T>
   int alloc(T** out, size_t count) {
     void* p = nullptr;
-    MMSBM_CUDA(cudaMalloc(&p, count ? count * sizeof(T) : 16));
+    MMSBM_CUDA(cudaMallocAsync(&p, count ? count * sizeof(T) : 16, st));
     ptrs.push_back(p);
     *out = static_cast<T*>(p);
     return 0;
@@ -68,12 +74,33 @@ struct Scope {
       set_error("no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
       return MMSBM_ENODEV;
     }
+    int dev = 0;
+    MMSBM_CUDA(cudaGetDevice(&dev));
+    cudaMemPool_t pool;
+    MMSBM_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t keep = UINT64_MAX;
+    MMSBM_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     MMSBM_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     return 0;
   }
 };
 
 #define TRY(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
+
+// MMSBM_TRACE=1: wall-clock of the stages of a host call on stderr (synchronises between stages)
+struct Trace {
+  bool on;
+  cudaStream_t st;
+  std::chrono::steady_clock::time_point t0;
+  explicit Trace(cudaStream_t s) : on(getenv("MMSBM_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[mmsbm] %-22s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 struct DevTriples { int32_t *u, *i, *r; };
 
@@ -163,6 +190,19 @@ extern "C" int mmsbm_device_count(void) {
     return MMSBM_ENODEV;
   }
   return n;
+}
+
+extern "C" int mmsbm_split_triples(const int64_t* data, int64_t N, int32_t U, int32_t I, int32_t R,
+                                   int32_t* u, int32_t* i, int32_t* r, int32_t* bad, void* stream) {
+  MMSBM_REQUIRE(N >= 0 && U > 0 && I > 0 && bad && (N == 0 || (data && u && i && r)), MMSBM_EINVAL,
+                "mmsbm_split_triples: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MMSBM_CUDA(cudaMemsetAsync(bad, 0, sizeof(int32_t), st));
+  if (N > 0) {
+    split_triples_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(data, N, U, I, R, u, i, r, bad);
+    MMSBM_LAUNCH_CHECK("split_triples_kernel");
+  }
+  return 0;
 }
 
 extern "C" int mmsbm_host_compute_omegas(const int64_t* data, int64_t N, const double* theta, int32_t U,
@@ -261,8 +301,11 @@ extern "C" int mmsbm_host_fit(const int64_t* data, int64_t N, int32_t U, int32_t
   MMSBM_REQUIRE(S > 0 && iterations >= 0 && theta_out && eta_out && pr_out && lik_out, MMSBM_EINVAL,
                 "mmsbm_host_fit: bad argument");
   Scope sc; TRY(sc.open());
+  Trace tr(sc.st);
   DevTriples t; TRY(upload_triples(sc, data, N, U, I, R, &t));
+  tr.mark("rows H2D + split");
   DevGraph g; TRY(build_graph(sc, t, N, U, I, R, &g));
+  tr.mark("index build");
   const int ldk = row_stride(K), ldl = row_stride(L);
   const size_t prn = (size_t)S * K * L * R;
   double *tha, *eta_a, *pra, *thb, *etb, *prb, *dlik;
@@ -277,15 +320,19 @@ extern "C" int mmsbm_host_fit(const int64_t* data, int64_t N, int32_t U, int32_t
   TRY(mmsbm_likelihood_workspace_bytes(U, S, &lwsb));
   char *ws, *lws;
   TRY(sc.alloc(&ws, wsb)); TRY(sc.alloc(&lws, lwsb));
+  tr.mark("params H2D + alloc");
   TRY(mmsbm_em_run(g.useg, g.uadj, g.udeg, g.iseg, g.iadj, g.ideg, N, U, I, R, K, L, S, iterations, tha,
                    eta_a, pra, thb, etb, prb, ws, wsb, sc.st));
+  tr.mark("EM iterations");
   const bool in_a = (iterations % 2) == 0;
   double* th = in_a ? tha : thb; double* et = in_a ? eta_a : etb; double* pr = in_a ? pra : prb;
   TRY(mmsbm_likelihood(g.useg, g.uadj, N, U, I, R, K, L, S, th, et, pr, dlik, lws, lwsb, sc.st));
+  tr.mark("likelihood");
   TRY(download_rows(sc, th, (size_t)S * U, K, theta_out));
   TRY(download_rows(sc, et, (size_t)S * I, L, eta_out));
   MMSBM_CUDA(cudaMemcpyAsync(pr_out, pr, prn * 8, cudaMemcpyDeviceToHost, sc.st));
   MMSBM_CUDA(cudaMemcpyAsync(lik_out, dlik, (size_t)S * 8, cudaMemcpyDeviceToHost, sc.st));
   MMSBM_CUDA(cudaStreamSynchronize(sc.st));
+  tr.mark("results D2H");
   return 0;
 }

@@ -14,68 +14,104 @@ constexpr int kLikCtas = 148 * 4;   // persistent CTAs per run
 
 // ---- likelihood ----------------------------------------------------------------------------
 // sum_n sum_kl w~ (log w~ - log S~_n), w~ = max(theta_k eta_l pr_klr, eps), S~ = max(sum w, eps).
-// Not factorisable (the clamp and the log act on each (k,l)), so every rating costs K*L logs.
-// One warp walks whole user segments of the (user, rating)-grouped index: theta_u is staged
-// once per user, the rating level is implied by the group; lanes own l, the loop runs over k.
+// The clamp acts on each (k,l), so every rating costs K*L element visits; what can be saved is
+// the logarithm: for w >= eps, log w = log theta_k + log eta_l + log pr_klr (three table values,
+// exact to rounding), for w < eps it is the constant log eps.  One log per (rating, l) remains.
+// Per rating: sum_kl w~ log w~ - log S~ * sum_kl w~, in a single sweep over k.
+// One warp walks whole user segments of the (user, level)-grouped index: theta_u and its logs
+// are staged once per user, the level is implied by the group; lanes own l, the loop runs over k.
 struct LikArgs {
   const int32_t* useg; const int32_t* uadj;
   const double* theta; const double* eta; const double* pr;
   double* partial;      // [S][kLikCtas*kLikWarps]
+  double* tables;       // [S][2][R][K][L] in global memory when they do not fit shared memory
   int U, I, R, K, L, ldk, ldl;
 };
+
+// pr and log pr in [R][K][L] order (global-memory variant of the tables)
+__global__ void lik_tables_kernel(const double* pr, int K, int L, int R, double* tables) {
+  const int run = blockIdx.y, n = K * L * R;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int kl = t / R, r = t - kl * R;
+  const double v = __ldg(pr + (size_t)run * n + t);
+  double* base = tables + (size_t)run * 2 * n;
+  base[(size_t)r * K * L + kl] = v;
+  base[(size_t)n + (size_t)r * K * L + kl] = log(v);
+}
 
 __global__ void __launch_bounds__(kLikWarps * 32) likelihood_kernel(const LikArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int K = A.K, L = A.L, R = A.R;
-  double* Pq = reinterpret_cast<double*>(smem_raw);          // [R][K][L]
-  double* th_s = Pq + (size_t)R * K * L;                     // [warps][K]
+  const double kLogEps = log(kEps);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int run = blockIdx.y;
-  const double* prs = A.pr + (size_t)run * K * L * R;
-  for (int t = threadIdx.x; t < K * L * R; t += blockDim.x) {
-    int kl = t / R, r = t - kl * R;
-    Pq[(size_t)r * K * L + kl] = __ldg(prs + t);
+  const double* Pq;                                          // [R][K][L]
+  const double* Lq;                                          // [R][K][L]  log pr
+  double* th_s;                                              // [warps][2][K]  theta, log theta
+  if (A.tables) {                                            // tables too large for shared memory
+    Pq = A.tables + (size_t)run * 2 * K * L * R;
+    Lq = Pq + (size_t)K * L * R;
+    th_s = reinterpret_cast<double*>(smem_raw);
+  } else {
+    double* Ps = reinterpret_cast<double*>(smem_raw);
+    double* Ls = Ps + (size_t)R * K * L;
+    th_s = Ls + (size_t)R * K * L;
+    const double* prs = A.pr + (size_t)run * K * L * R;
+    for (int t = threadIdx.x; t < K * L * R; t += blockDim.x) {
+      int kl = t / R, r = t - kl * R;
+      const double v = __ldg(prs + t);
+      Ps[(size_t)r * K * L + kl] = v;
+      Ls[(size_t)r * K * L + kl] = log(v);
+    }
+    __syncthreads();
+    Pq = Ps; Lq = Ls;
   }
-  __syncthreads();
-  double* th = th_s + warp * K;
+  double* th = th_s + warp * 2 * K;
+  double* lth = th + K;
   const double* theta_run = A.theta + (size_t)run * A.U * A.ldk;
   const double* eta_run = A.eta + (size_t)run * A.I * A.ldl;
   const int gw = blockIdx.x * kLikWarps + warp, nw = gridDim.x * kLikWarps;
   double acc = 0.0;
   for (int u = gw; u < A.U; u += nw) {
     __syncwarp();
-    for (int k = lane; k < K; k += 32) th[k] = __ldg(theta_run + (size_t)u * A.ldk + k);
+    for (int k = lane; k < K; k += 32) {
+      const double v = __ldg(theta_run + (size_t)u * A.ldk + k);
+      th[k] = v;
+      lth[k] = log(v);
+    }
     __syncwarp();
     for (int r = 0; r < R; ++r) {
       const int lo = __ldg(A.useg + (size_t)u * R + r), hi = __ldg(A.useg + (size_t)u * R + r + 1);
       const double* Pr = Pq + (size_t)r * K * L;
+      const double* Lr = Lq + (size_t)r * K * L;
       for (int j = lo; j < hi; ++j) {
         const int item = __ldg(A.uadj + j);
         const double* erow = eta_run + (size_t)item * A.ldl;
-        double tot = 0.0;
+        double tot = 0.0, s1 = 0.0, s2 = 0.0;   // sum w, sum w~ log w~, sum w~
         for (int l0 = 0; l0 < L; l0 += 32) {
           const int l = l0 + lane;
           if (l < L) {
             const double e = __ldg(erow + l);
-            for (int k = 0; k < K; ++k) tot += __dmul_rn(__dmul_rn(th[k], e), Pr[k * L + l]);
-          }
-        }
-        tot = warp_sum(tot);
-        const double ls = log(fmax(tot, kEps));
-        for (int l0 = 0; l0 < L; l0 += 32) {
-          const int l = l0 + lane;
-          if (l < L) {
-            const double e = __ldg(erow + l);
+            const double le = log(e);
             for (int k = 0; k < K; ++k) {
-              const double w = fmax(__dmul_rn(__dmul_rn(th[k], e), Pr[k * L + l]), kEps);
-              acc += __dsub_rn(__dmul_rn(w, log(w)), __dmul_rn(w, ls));
+              const double w = __dmul_rn(__dmul_rn(th[k], e), Pr[k * L + l]);   // reference order
+              const bool small = w < kEps;
+              const double wc = small ? kEps : w;
+              const double lw = small ? kLogEps : (lth[k] + le) + Lr[k * L + l];
+              tot += w;
+              s1 = fma(wc, lw, s1);
+              s2 += wc;
             }
           }
         }
+        tot = warp_sum(tot);
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        acc += s1 - log(fmax(tot, kEps)) * s2;
       }
     }
   }
-  acc = warp_sum(acc);
   if (lane == 0) A.partial[(size_t)run * nw + gw] = acc;
 }
 
@@ -236,9 +272,11 @@ constexpr int kStatBlocks = 296;
 
 using namespace mmsbm;
 
+constexpr size_t kLikTableBytes = 512 * 1024;   // room for [2][R][K][L] per run when spilled to global
+
 extern "C" int mmsbm_likelihood_workspace_bytes(int32_t U, int32_t S, size_t* bytes) {
   MMSBM_REQUIRE(bytes && U > 0 && S > 0, MMSBM_EINVAL, "mmsbm_likelihood_workspace_bytes: bad argument");
-  *bytes = align_up((size_t)S * kLikCtas * kLikWarps * 8) + 256;
+  *bytes = align_up((size_t)S * kLikCtas * kLikWarps * 8) + align_up((size_t)S * kLikTableBytes) + 256;
   return 0;
 }
 
@@ -255,9 +293,18 @@ extern "C" int mmsbm_likelihood(const int32_t* useg, const int32_t* uadj, int64_
   const int nw = kLikCtas * kLikWarps;
   double* partial = arena.take<double>((size_t)S * nw);
   MMSBM_REQUIRE(partial, MMSBM_ENOMEM, "mmsbm_likelihood: workspace too small");
-  LikArgs a{useg, uadj, theta, eta, pr, partial, U, I, R, K, L, row_stride(K), row_stride(L)};
-  size_t smem = ((size_t)R * K * L + (size_t)kLikWarps * K) * 8;
-  MMSBM_REQUIRE(smem <= 227 * 1024, MMSBM_ERANGE, "mmsbm_likelihood: K*L*R too large for shared memory");
+  LikArgs a{useg, uadj, theta, eta, pr, partial, nullptr, U, I, R, K, L, row_stride(K), row_stride(L)};
+  size_t smem = (2 * (size_t)R * K * L + 2 * (size_t)kLikWarps * K) * 8;
+  if (smem > 200 * 1024) {                       // keep the two tables in global memory (L2 resident)
+    const size_t tb = 2 * (size_t)R * K * L * 8;
+    MMSBM_REQUIRE(tb <= kLikTableBytes, MMSBM_ERANGE, "mmsbm_likelihood: K*L*R = %d too large", K * L * R);
+    a.tables = arena.take<double>((size_t)S * 2 * R * K * L);
+    MMSBM_REQUIRE(a.tables, MMSBM_ENOMEM, "mmsbm_likelihood: workspace too small");
+    const int n = K * L * R;
+    lik_tables_kernel<<<dim3((n + 255) / 256, S), 256, 0, st>>>(pr, K, L, R, a.tables);
+    MMSBM_LAUNCH_CHECK("lik_tables_kernel");
+    smem = 2 * (size_t)kLikWarps * K * 8;
+  }
   MMSBM_CUDA(cudaFuncSetAttribute(likelihood_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   likelihood_kernel<<<dim3(kLikCtas, S), kLikWarps * 32, smem, st>>>(a);
   MMSBM_LAUNCH_CHECK("likelihood_kernel");

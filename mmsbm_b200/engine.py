@@ -29,17 +29,23 @@ class Engine:
         self.N = int(data.shape[0])
         self.U, self.I, self.R, self.K, self.L = int(n_users), int(n_items), int(n_levels), int(K), int(L)
         self.ldk, self.ldl = self.lib.mmsbm_row_stride(self.K), self.lib.mmsbm_row_stride(self.L)
-        if self.N:
-            lo, hi = data.min(axis=0), data.max(axis=0)
-            if lo.min() < 0 or hi[0] >= self.U or hi[1] >= self.I or hi[2] >= self.R:
-                raise ValueError("data holds an id outside [0,U) x [0,I) x [0,R)")
         self.S = 0
         self.theta = self.eta = self.pr = None
         self._alt = None
         self._ws = None
         with torch.cuda.device(self.device):
-            cols = np.ascontiguousarray(data.T.astype(np.int32, copy=False))   # host marshalling
-            self.cols = torch.from_numpy(cols).to(self.device, non_blocking=False)  # [3][N] int32
+            # the int64 [N,3] rows go up as they are; the int32 split and the id range check
+            # run on the device (mmsbm_split_triples)
+            raw = torch.from_numpy(np.ascontiguousarray(data, dtype=np.int64)).to(self.device)
+            self.cols = torch.empty((3, max(self.N, 1)), dtype=torch.int32, device=self.device)
+            bad = torch.zeros(1, dtype=torch.int32, device=self.device)
+            _lib.check(self.lib.mmsbm_split_triples(
+                raw.data_ptr(), self.N, self.U, self.I, self.R, self.cols[0].data_ptr(),
+                self.cols[1].data_ptr(), self.cols[2].data_ptr(), bad.data_ptr(), self._stream()),
+                "split_triples")
+            if int(bad.item()):
+                raise ValueError("data holds an id outside [0,U) x [0,I) x [0,R)")
+            del raw
             self._build_graph()
 
     # ------------------------------------------------------------------ plumbing

@@ -165,7 +165,9 @@ def test_batched_runs_one_iteration_vs_oracle(K, L, R, S, heavy):
         rt, re_, rp = orc.em_iteration(data, theta[s], eta[s], pr[s], fu, fi, chunk=20000)
         worst = max(worst, rel_err(th[s], rt), rel_err(et[s], re_), rel_err(prn[s], rp))
         want = sum(orc.likelihood(data[lo:lo + 20000], rt, re_, rp) for lo in range(0, N, 20000))
-        assert abs(lik[s] - want) <= LIK_TOL * abs(want)
+        # 1e-8 relative (north_star); the absolute floor covers the degenerate K=L=1 case where
+        # the reference's value is exactly 0 and only rounding noise (~1e-16 per element) is left
+        assert abs(lik[s] - want) <= LIK_TOL * abs(want) + 1e-15 * N * K * L
         # size-independent invariants of one EM step
         np.testing.assert_allclose(th[s].sum(axis=1), 1.0, rtol=1e-12)
         np.testing.assert_allclose(et[s].sum(axis=1), 1.0, rtol=1e-12)
