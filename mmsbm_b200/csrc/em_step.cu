@@ -391,7 +391,7 @@ static int segs_per_cta_for(int nseg) {
   // dynamic scheduling inside a CTA needs several segments per warp to balance; keep >= ~600
   // CTAs per run so that the grid still covers 148 SMs x 3 several times over
   int spc = nseg / 592;
-  if (spc < 2 * kWarps) spc = 2 * kWarps;
+  if (spc < kWarps) spc = kWarps;               // small problems: one segment per warp, most CTAs
   if (spc > 64) spc = 64;
   const int e = env_int("MMSBM_SPC", 0);
   return e > 0 ? e : spc;
@@ -646,12 +646,48 @@ extern "C" int mmsbm_em_run(const int32_t* useg, const int32_t* uadj, const int3
                             double* pr_a, double* theta_b, double* eta_b, double* pr_b, void* ws,
                             size_t ws_bytes, void* stream) {
   MMSBM_REQUIRE(iterations >= 0, MMSBM_EINVAL, "mmsbm_em_run: negative iteration count");
-  for (int it = 0; it < iterations; ++it) {
-    const bool fwd = (it & 1) == 0;
-    int rc = mmsbm_em_step(useg, uadj, udeg, iseg, iadj, ideg, N, U, I, R, K, L, S,
-                           fwd ? theta_a : theta_b, fwd ? eta_a : eta_b, fwd ? pr_a : pr_b,
-                           fwd ? theta_b : theta_a, fwd ? eta_b : eta_a, fwd ? pr_b : pr_a, 0, ws,
-                           ws_bytes, stream);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto step = [&](bool fwd) {
+    return mmsbm_em_step(useg, uadj, udeg, iseg, iadj, ideg, N, U, I, R, K, L, S,
+                         fwd ? theta_a : theta_b, fwd ? eta_a : eta_b, fwd ? pr_a : pr_b,
+                         fwd ? theta_b : theta_a, fwd ? eta_b : eta_a, fwd ? pr_b : pr_a, 0, ws,
+                         ws_bytes, stream);
+  };
+  int done = 0;
+  // Launch-bound sizes (a few 10 us of kernels per iteration): capture one a->b->a pair of
+  // iterations into a CUDA graph and replay it; the graph lives only inside this call.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  const bool small = (double)N * S < 5.0e7 && getenv("MMSBM_NO_GRAPH") == nullptr;
+  if (small && iterations >= 8 && st != nullptr && cudaStreamIsCapturing(st, &cap) == cudaSuccess &&
+      cap == cudaStreamCaptureStatusNone) {
+    int rc = step(true);                       // first pair uncaptured: sets function attributes
+    if (rc == 0) rc = step(false);
+    if (rc) return rc;
+    done = 2;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    const int64_t l0 = mmsbm_launch_count();
+    MMSBM_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = step(true);
+    if (rc == 0) rc = step(false);
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    const int per_pair = (int)(mmsbm_launch_count() - l0);
+    count_launch(-per_pair);                   // the capture itself launched nothing
+    if (rc == 0 && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc) return rc;
+    if (e == cudaSuccess && exec) {
+      for (; done + 2 <= iterations; done += 2) {
+        MMSBM_CUDA(cudaGraphLaunch(exec, st));
+        count_launch(per_pair);
+      }
+      cudaGraphExecDestroy(exec);              // freed asynchronously once the replays finish
+    } else {
+      (void)cudaGetLastError();                // graph path unavailable: fall through to plain launches
+    }
+  }
+  for (int it = done; it < iterations; ++it) {
+    int rc = step((it & 1) == 0);
     if (rc) return rc;
   }
   return 0;
