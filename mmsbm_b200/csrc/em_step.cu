@@ -75,6 +75,7 @@ struct GemmArgs {
   const double* own;    // EPI: [S][M][N]
   const int32_t* deg;   // EPI: [M]
   int M, N, Kd, lda, rg, normalize;
+  int b_resident;       // whole B staged once (fits shared memory) or one k-slab at a time
 };
 
 template <bool EPI>
@@ -82,18 +83,17 @@ __global__ void __launch_bounds__(kGemmThreads) small_gemm_kernel(const GemmArgs
   constexpr int TR = kGemmTR;                  // rows of the register tile (columns: 4)
   extern __shared__ __align__(32) unsigned char smem_raw[];
   const int BM = TR * g.rg, AS = kGemmBK + 2;
-  double* Bs = reinterpret_cast<double*>(smem_raw);          // [Kd][N]   whole B, staged once
-  double* As = Bs + (size_t)g.Kd * g.N;                      // [BM][AS]  one k-slab of a row tile
+  double* Bs = reinterpret_cast<double*>(smem_raw);          // [Kd][N] whole B, or [kGemmBK][N] slab
+  double* As = Bs + (size_t)(g.b_resident ? g.Kd : kGemmBK) * g.N;   // [BM][AS] k-slab of a row tile
   const int run = blockIdx.y;
   const int ncg = g.N >> 2, half = g.N >> 1;
   const int rgid = threadIdx.x / ncg, cg = threadIdx.x - rgid * ncg;
   const bool active = rgid < g.rg;
   const double* A = g.A + (size_t)run * g.M * g.lda;
-  {
-    const double2* B2 = reinterpret_cast<const double2*>(g.B + (size_t)run * g.Kd * g.N);
-    double2* Bs2 = reinterpret_cast<double2*>(Bs);
+  const double2* B2 = reinterpret_cast<const double2*>(g.B + (size_t)run * g.Kd * g.N);
+  double2* Bs2 = reinterpret_cast<double2*>(Bs);
+  if (g.b_resident)
     for (int t = threadIdx.x; t < (g.Kd * g.N) >> 1; t += kGemmThreads) Bs2[t] = __ldg(B2 + t);
-  }
   const int n_tiles = (g.M + BM - 1) / BM;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int row0 = tile * BM;
@@ -113,13 +113,16 @@ __global__ void __launch_bounds__(kGemmThreads) small_gemm_kernel(const GemmArgs
         if (row0 + m < g.M) v = __ldg(reinterpret_cast<const double2*>(A + (size_t)(row0 + m) * g.lda + k0) + p2);
         *reinterpret_cast<double2*>(As + m * AS + 2 * p2) = v;
       }
+      if (!g.b_resident)
+        for (int t = threadIdx.x; t < (bk * g.N) >> 1; t += kGemmThreads)
+          Bs2[t] = __ldg(B2 + (((size_t)k0 * g.N) >> 1) + t);
       __syncthreads();
       if (active) {
         // thread tile: rows TR*rgid.., columns {2cg, 2cg+1, N/2+2cg, N/2+2cg+1}: consecutive
         // threads read consecutive 16-byte pieces of a B row (no bank conflicts); the A reads of
         // a warp are (nearly) uniform, i.e. broadcasts
         const double* ap = As + (size_t)(TR * rgid) * AS;
-        const double* bp = Bs + (size_t)k0 * g.N + 2 * cg;
+        const double* bp = Bs + (size_t)(g.b_resident ? k0 : 0) * g.N + 2 * cg;
         for (int kk = 0; kk < bk; kk += 2) {
           const double2 b00 = *reinterpret_cast<const double2*>(bp + (size_t)kk * g.N);
           const double2 b01 = *reinterpret_cast<const double2*>(bp + (size_t)kk * g.N + half);
@@ -436,6 +439,8 @@ static int launch_gemm(GemmArgs g, int n_runs, cudaStream_t st) {
   g.rg = rg;
   const int BM = kGemmTR * rg;
   size_t smem = ((size_t)g.Kd * g.N + (size_t)BM * (kGemmBK + 2)) * 8;
+  g.b_resident = smem <= 200 * 1024;
+  if (!g.b_resident) smem = ((size_t)kGemmBK * g.N + (size_t)BM * (kGemmBK + 2)) * 8;
   MMSBM_REQUIRE(smem <= 227 * 1024, MMSBM_ERANGE,
                 "small gemm needs %zu bytes of shared memory (K*L*R too large)", smem);
   auto kern = small_gemm_kernel<EPI>;
@@ -464,7 +469,7 @@ static int launch_w(const double* own, const double* pw, double* W, int M, int L
   MMSBM_ROW_W(4) MMSBM_ROW_W(8) MMSBM_ROW_W(12) MMSBM_ROW_W(16) MMSBM_ROW_W(20) MMSBM_ROW_W(24)
   MMSBM_ROW_W(28) MMSBM_ROW_W(32)
 #undef MMSBM_ROW_W
-  GemmArgs g{own, pw, W, nullptr, nullptr, M, RNB, LD, LD, 0, 0};
+  GemmArgs g{own, pw, W, nullptr, nullptr, M, RNB, LD, LD, 0, 0, 0};
   return launch_gemm<false>(g, n_runs, st);
 }
 
@@ -482,7 +487,7 @@ static int launch_n(const double* G, const double* pn, const double* own, const 
   MMSBM_ROW_N(4) MMSBM_ROW_N(8) MMSBM_ROW_N(12) MMSBM_ROW_N(16) MMSBM_ROW_N(20) MMSBM_ROW_N(24)
   MMSBM_ROW_N(28) MMSBM_ROW_N(32)
 #undef MMSBM_ROW_N
-  GemmArgs g{G, pn, out, own, deg, M, LD, RNB, RNB, 0, normalize};
+  GemmArgs g{G, pn, out, own, deg, M, LD, RNB, RNB, 0, normalize, 0};
   return launch_gemm<true>(g, n_runs, st);
 }
 

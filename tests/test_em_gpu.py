@@ -147,7 +147,7 @@ def test_fixture_one_and_ten_iterations(golden_dir):
 
 
 @pytest.mark.parametrize("K,L,R,S", [(10, 10, 5, 3), (20, 20, 5, 2), (7, 5, 4, 1), (3, 32, 6, 2), (33, 9, 5, 1),
-                                     (1, 1, 2, 1), (64, 48, 5, 1)])
+                                     (1, 1, 2, 1), (64, 48, 5, 1), (130, 70, 3, 1), (12, 28, 10, 2)])
 @pytest.mark.parametrize("heavy", [False, True])
 def test_batched_runs_one_iteration_vs_oracle(K, L, R, S, heavy):
     from mmsbm_b200.engine import Engine
@@ -174,6 +174,57 @@ def test_batched_runs_one_iteration_vs_oracle(K, L, R, S, heavy):
         np.testing.assert_allclose(prn[s].sum(axis=2), 1.0, rtol=1e-12)
     print(f"K={K} L={L} R={R} S={S} heavy={heavy}: worst rel err {worst:.3e}")
     assert worst < PARAM_TOL
+
+
+def test_one_giant_segment_and_many_empty_levels():
+    """A user holding most of the ratings (one warp walks a 40k-row segment) and rating levels
+    that almost never occur (empty (segment, level) groups everywhere)."""
+    from mmsbm_b200.engine import Engine
+    g = np.random.default_rng(61)
+    N, U, I, K, L, R = 50000, 300, 2000, 10, 10, 9
+    data = random_triples(67, N, U, I, R)
+    data[U:45000, 0] = 7                                    # user 7 owns ~90 % of the rows
+    data[R:, 2] = g.choice(R, size=N - R, p=[0.45, 0.45, 0.04, 0.03, 0.01, 0.01, 0.005, 0.004, 0.001])
+    theta, eta, pr = random_params(71, U, I, K, L, R, S=2)
+    e = Engine(data, U, I, R, K, L)
+    e.set_params(theta, eta, pr)
+    e.run(1)
+    th, et, prn = e.get_params()
+    fu, fi = orc.degree_factors(data, K, L)
+    for s in range(2):
+        rt, re_, rp = orc.em_iteration(data, theta[s], eta[s], pr[s], fu, fi)
+        assert max(rel_err(th[s], rt), rel_err(et[s], re_), rel_err(prn[s], rp)) < PARAM_TOL
+
+
+def test_unsupported_shapes_fail_loudly():
+    from mmsbm_b200._lib import MmsbmError
+    from mmsbm_b200.engine import Engine
+    data = random_triples(73, 2000, 30, 20, 40)
+    theta, eta, pr = random_params(79, 30, 20, 3, 3, 40, S=1)
+    e = Engine(data, 30, 20, 40, 3, 3)
+    e.set_params(theta, eta, pr)
+    with pytest.raises(MmsbmError):                          # R > 31 rating levels
+        e.run(1)
+    with pytest.raises(ValueError):
+        Engine(np.array([[0, 0, 0], [5, 0, 0]]), 3, 2, 2, 2, 2)   # user id out of range
+
+
+def test_debug_mode_and_dropped_test_rows(tmp_path, monkeypatch, caplog):
+    """debug=True logs the likelihood every 50 iterations (src/mmsbm.py:252-254); test rows with
+    ids unseen in training are dropped with the reference's warning."""
+    import logging
+    import pandas as pd
+    monkeypatch.chdir(tmp_path)
+    from mmsbm_b200 import MMSBM
+    mm = MMSBM(2, 2, iterations=60, sampling=2, seed=4, debug=True)
+    mm.fit(mock_data(1), silent=True)
+    assert len(mm.results) == 2 and all(np.isfinite(r["likelihood"]) for r in mm.results)
+    test = pd.concat([mock_data(2, n=20), pd.DataFrame({"users": ["ghost"], "items": ["item1"], "ratings": [3]})])
+    logging.getLogger("MMSBM").propagate = True
+    with caplog.at_level(logging.WARNING, logger="MMSBM"):
+        pred = mm.predict(test)
+    assert pred.shape == (20, 5)
+    assert any("ghost" in r.getMessage() for r in caplog.records)
 
 
 def test_raw_sums_flags_and_finalize():
