@@ -51,12 +51,24 @@ R = 5
 FALLBACK_HBM_GBS = 6650.0   # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
-def synth_triples(U, I, N, seed=0):
-    """Uniform ids like the reference's benchmark_mmsbm.py:23-31; every id forced to appear."""
+def _zipf_ids(g, n_ids, size):
+    """Heavy-tailed ids: P(id = k) ~ 1/(k+1) (Zipf exponent 1), by inverse-CDF sampling."""
+    cdf = np.cumsum(1.0 / np.arange(1, n_ids + 1))
+    cdf /= cdf[-1]
+    return np.searchsorted(cdf, g.random(size), side="left").astype(np.int64)
+
+
+def synth_triples(U, I, N, seed=0, ids="uniform"):
+    """Uniform ids like the reference's benchmark_mmsbm.py:23-31, or Zipf-like heavy-tailed ids
+    (SURVEY.md 8d); every id forced to appear."""
     g = np.random.default_rng(seed)
     data = np.empty((N, 3), dtype=np.int64)
-    data[:, 0] = g.integers(0, U, N)
-    data[:, 1] = g.integers(0, I, N)
+    if ids == "zipf":
+        data[:, 0] = _zipf_ids(g, U, N)
+        data[:, 1] = _zipf_ids(g, I, N)
+    else:
+        data[:, 0] = g.integers(0, U, N)
+        data[:, 1] = g.integers(0, I, N)
     data[:, 2] = g.integers(0, R, N)
     data[:U, 0] = np.arange(U)
     data[:I, 1] = np.arange(I)
@@ -235,7 +247,7 @@ def run_b200_arm(args, shape):
     lib = _lib.load(require_device=True)
 
     t0 = time.perf_counter()
-    data = synth_triples(U, I, N, seed=0)
+    data = synth_triples(U, I, N, seed=0, ids=args.ids)
     seeds = np.random.default_rng(1).bit_generator._seed_seq.spawn(S * world)[rank * S:(rank + 1) * S]
     th0, et0, pr0 = seeded_inits(data, U, I, K, L, seeds)
     gen_s = time.perf_counter() - t0
@@ -351,7 +363,7 @@ def run_b200_arm(args, shape):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": args.workload, "users": U, "items": I, "ratings": N, "K": K, "L": L, "R": R,
-                       "sampling_per_gpu": S, "iterations_per_step": T, "ids": "uniform, seed 0",
+                       "sampling_per_gpu": S, "iterations_per_step": T, "ids": f"{args.ids}, seed 0",
                        "init": "reference seeded init, model seed 1",
                        "parallelism": f"runs sharded over {world} GPU(s), no data-path collective",
                        "l2": "no explicit flush: one iteration touches the parameters of all runs and both "
@@ -374,6 +386,7 @@ def main():
     ap.add_argument("--workload", default="ml20m", choices=sorted(WORKLOADS))
     ap.add_argument("--iters-per-step", type=int, default=400)
     ap.add_argument("--cpu-rows", type=int, default=200_000)
+    ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -34,7 +34,9 @@
  *         uadj [N]      item id of each row, in (u, r, row) order
  *         uperm[N]      original row index (== stable argsort of u*R+r)
  *         udeg [U]      number of rows of user u
- *   and iseg/iadj/iperm/ideg symmetrically (iadj holds user ids).
+ *   and iseg/iadj/iperm/ideg symmetrically (iadj holds user ids);
+ *         usched, isched   work schedule of the hot kernel (pieces of at most MMSBM_PIECE_LEN
+ *                          ratings per warp, built from the degrees; opaque to the caller)
  * This holds what the reference keeps as per-id row lists
  * (src/mmsbm.py:100-122): group (a,r) = _user_indices[a] & _rating_indices[r].
  */
@@ -48,7 +50,11 @@
 extern "C" {
 #endif
 
-#define MMSBM_ABI_VERSION 1
+#define MMSBM_ABI_VERSION 2
+
+/* a warp of the hot kernel processes at most this many ratings of one segment at a time; longer
+ * segments are cut into pieces whose partial sums are added in piece order (see usched/isched) */
+#define MMSBM_PIECE_LEN 2048
 
 #define MMSBM_EINVAL  (-1)   /* bad argument (null pointer, size out of range)      */
 #define MMSBM_ERANGE  (-2)   /* shape not supported (K or L > 256, R > 31, id*R >= 2^31) */
@@ -79,19 +85,23 @@ int mmsbm_split_triples(const int64_t* data_dev, int64_t n_ratings, int32_t n_us
 /* ---- a8: index structure, replaces MMSBM._prepare_objects (src/mmsbm.py:93-122) -------- */
 int mmsbm_graph_workspace_bytes(int64_t n_ratings, int32_t n_users, int32_t n_items,
                                 int32_t n_levels, size_t* bytes);
+/* int32 elements of the work schedule of one side (usched: n_segments = U, isched: = I) */
+int mmsbm_sched_elems(int64_t n_ratings, int32_t n_segments, int64_t* elems);
 int mmsbm_graph_build(const int32_t* user_dev, const int32_t* item_dev, const int32_t* level_dev,
                       int64_t n_ratings, int32_t n_users, int32_t n_items, int32_t n_levels,
                       int32_t* useg_dev, int32_t* uadj_dev, int32_t* uperm_dev, int32_t* udeg_dev,
                       int32_t* iseg_dev, int32_t* iadj_dev, int32_t* iperm_dev, int32_t* ideg_dev,
+                      int32_t* usched_dev, int32_t* isched_dev,
                       void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---- a2+a3+a4: one EM iteration for S runs, replaces update_coefficients
  *      (src/kernels_numpy.py:43-79) + normalize_with_d x2 + normalize_with_self
  *      (src/expectation_maximization.py:118-155), i.e. the loop body src/mmsbm.py:244-250 --- */
-int mmsbm_em_workspace_bytes(int32_t n_users, int32_t n_items, int32_t n_levels,
+int mmsbm_em_workspace_bytes(int64_t n_ratings, int32_t n_users, int32_t n_items, int32_t n_levels,
                              int32_t K, int32_t L, int32_t n_runs, size_t* bytes);
 int mmsbm_em_step(const int32_t* useg_dev, const int32_t* uadj_dev, const int32_t* udeg_dev,
                   const int32_t* iseg_dev, const int32_t* iadj_dev, const int32_t* ideg_dev,
+                  const int32_t* usched_dev, const int32_t* isched_dev,
                   int64_t n_ratings, int32_t n_users, int32_t n_items, int32_t n_levels,
                   int32_t K, int32_t L, int32_t n_runs,
                   const double* theta_dev, const double* eta_dev, const double* pr_dev,
@@ -102,6 +112,7 @@ int mmsbm_em_step(const int32_t* useg_dev, const int32_t* uadj_dev, const int32_
  * pr accumulate, pr finalize} */
 int mmsbm_em_step_profiled(const int32_t* useg_dev, const int32_t* uadj_dev, const int32_t* udeg_dev,
                            const int32_t* iseg_dev, const int32_t* iadj_dev, const int32_t* ideg_dev,
+                           const int32_t* usched_dev, const int32_t* isched_dev,
                            int64_t n_ratings, int32_t n_users, int32_t n_items, int32_t n_levels,
                            int32_t K, int32_t L, int32_t n_runs,
                            const double* theta_dev, const double* eta_dev, const double* pr_dev,
@@ -113,6 +124,7 @@ int mmsbm_em_step_profiled(const int32_t* useg_dev, const int32_t* uadj_dev, con
  * Replaces the loop src/mmsbm.py:243-250. */
 int mmsbm_em_run(const int32_t* useg_dev, const int32_t* uadj_dev, const int32_t* udeg_dev,
                  const int32_t* iseg_dev, const int32_t* iadj_dev, const int32_t* ideg_dev,
+                 const int32_t* usched_dev, const int32_t* isched_dev,
                  int64_t n_ratings, int32_t n_users, int32_t n_items, int32_t n_levels,
                  int32_t K, int32_t L, int32_t n_runs, int32_t iterations,
                  double* theta_a_dev, double* eta_a_dev, double* pr_a_dev,

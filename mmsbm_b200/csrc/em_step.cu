@@ -43,6 +43,24 @@ constexpr int kGemmThreads = 256;
 constexpr int kGemmBK = 32;     // k-slab of the small GEMM (even)
 constexpr int kGemmTR = 4;      // rows per thread tile of the small GEMM
 
+// g rows of long segments: add the partial rows of their pieces in piece order
+__global__ void __launch_bounds__(128) segment_fixup_kernel(const SegArgs A) {
+  const int run = blockIdx.y, RNB = A.R * A.NBp;
+  const int n_long = __ldg(A.sched + 2);
+  const int32_t* long_seg = A.sched + 4 + 3 * A.pmax;
+  const int32_t* long_slot0 = long_seg + A.lmax;
+  for (int li = blockIdx.x; li < n_long; li += gridDim.x) {
+    const int sg = __ldg(long_seg + li), s0 = __ldg(long_slot0 + li), s1 = __ldg(long_slot0 + li + 1);
+    const double* src = A.partial + ((size_t)run * A.lmax + s0) * RNB;
+    double* dst = A.wg + ((size_t)run * A.nseg + sg) * RNB;
+    for (int o = threadIdx.x; o < RNB; o += blockDim.x) {
+      double acc = 0.0;
+      for (int k = 0; k < s1 - s0; ++k) acc += src[(size_t)k * RNB + o];
+      dst[o] = acc;
+    }
+  }
+}
+
 // ---- P in operand layout -------------------------------------------------------------------
 // For a side with owner dim NA (stride lda), neighbour dim NB (stride NBp), RNB = R*NBp and
 // o = r*NBp + b:   Pw[a][o] (lda x RNB)   Pn[o][a] (RNB x lda),  zero in every padded slot.
@@ -400,10 +418,11 @@ static int segs_per_cta_for(int nseg) {
   return e > 0 ? e : spc;
 }
 
-static int launch_segment_pass(SegArgs a, int64_t n_ratings, int n_runs, cudaStream_t st) {
+static int launch_segment_pass_impl(SegArgs a, int64_t n_ratings, int n_runs, cudaStream_t st) {
   PassShape sh = choose_shape(a.NBp, (double)n_ratings / (double)a.nseg);
   a.segs_per_cta = segs_per_cta_for(a.nseg);
-  const dim3 grid((a.nseg + a.segs_per_cta - 1) / a.segs_per_cta, n_runs);
+  // the piece count lives on the device; size the grid for its upper bound (CTAs past it exit)
+  const dim3 grid((unsigned)((a.pmax + a.segs_per_cta - 1) / a.segs_per_cta), n_runs);
   const size_t smem = seg_smem_bytes(a);
   MMSBM_REQUIRE(smem <= 227 * 1024, MMSBM_ERANGE,
                 "segment pass needs %zu bytes of shared memory (R=%d, row stride %d)", smem, a.R, a.NBp);
@@ -427,6 +446,15 @@ static int launch_segment_pass(SegArgs a, int64_t n_ratings, int n_runs, cudaStr
   const int rc = go(sh);
   if (rc == MMSBM_ERANGE) set_error("no segment-pass variant for G=%d CH=%d UN=%d", sh.G, sh.CH, sh.UN);
   return rc;
+}
+
+static int launch_segment_pass_and_fixup(SegArgs a, int64_t n_ratings, int n_runs, cudaStream_t st) {
+  int rc = launch_segment_pass_impl(a, n_ratings, n_runs, st);
+  if (rc) return rc;
+  const unsigned gx = (unsigned)(a.lmax < 592 ? a.lmax : 592);
+  segment_fixup_kernel<<<dim3(gx, n_runs), 128, 0, st>>>(a);
+  MMSBM_LAUNCH_CHECK("segment_fixup_kernel");
+  return 0;
 }
 
 template <bool EPI>
@@ -495,10 +523,11 @@ struct EmDims {
   int U, I, R, K, L, S, ldk, ldl, rnb_u, rnb_i;
   bool emit_items;   // the side with fewer segments carries the pr accumulation
   int nseg_e, NA_e, NBp_e;
-  size_t p_elems, wg_u_elems, wg_i_elems, partial_elems;
+  size_t p_elems, wg_u_elems, wg_i_elems, partial_elems, slots_u_elems, slots_i_elems;
+  int64_t lmax, pmax_u, pmax_i;
 };
 
-static EmDims em_dims(int U, int I, int R, int K, int L, int S) {
+static EmDims em_dims(int64_t N, int U, int I, int R, int K, int L, int S) {
   EmDims d;
   d.U = U; d.I = I; d.R = R; d.K = K; d.L = L; d.S = S;
   d.ldk = row_stride(K); d.ldl = row_stride(L);
@@ -511,6 +540,11 @@ static EmDims em_dims(int U, int I, int R, int K, int L, int S) {
   d.wg_u_elems = (size_t)S * U * d.rnb_u;
   d.wg_i_elems = (size_t)S * I * d.rnb_i;
   d.partial_elems = (size_t)S * kPrSlabs * d.NA_e * R * d.NBp_e;
+  d.lmax = N / MMSBM_PIECE_LEN + 1;                 // must match graph_build.cu
+  d.pmax_u = (int64_t)U + N / MMSBM_PIECE_LEN + 1;
+  d.pmax_i = (int64_t)I + N / MMSBM_PIECE_LEN + 1;
+  d.slots_u_elems = (size_t)S * d.lmax * d.rnb_u;
+  d.slots_i_elems = (size_t)S * d.lmax * d.rnb_i;
   return d;
 }
 
@@ -518,30 +552,30 @@ static EmDims em_dims(int U, int I, int R, int K, int L, int S) {
 
 using namespace mmsbm;
 
-extern "C" int mmsbm_em_workspace_bytes(int32_t U, int32_t I, int32_t R, int32_t K, int32_t L,
-                                        int32_t S, size_t* bytes) {
-  MMSBM_REQUIRE(bytes && U > 0 && I > 0 && R > 0 && K > 0 && L > 0 && S > 0, MMSBM_EINVAL,
+extern "C" int mmsbm_em_workspace_bytes(int64_t N, int32_t U, int32_t I, int32_t R, int32_t K,
+                                        int32_t L, int32_t S, size_t* bytes) {
+  MMSBM_REQUIRE(bytes && N >= 0 && U > 0 && I > 0 && R > 0 && K > 0 && L > 0 && S > 0, MMSBM_EINVAL,
                 "mmsbm_em_workspace_bytes: bad argument");
-  EmDims d = em_dims(U, I, R, K, L, S);
+  EmDims d = em_dims(N, U, I, R, K, L, S);
   *bytes = 4 * align_up(d.p_elems * 8) + align_up(d.wg_u_elems * 8) + align_up(d.wg_i_elems * 8) +
-           align_up(d.partial_elems * 8) + 256;
+           align_up(d.partial_elems * 8) + align_up(d.slots_u_elems * 8) + align_up(d.slots_i_elems * 8) + 256;
   return 0;
 }
 
 static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t* udeg,
                         const int32_t* iseg, const int32_t* iadj, const int32_t* ideg,
-                        int64_t N, int32_t U, int32_t I, int32_t R, int32_t K, int32_t L,
+                        const int32_t* usched, const int32_t* isched, int64_t N, int32_t U, int32_t I, int32_t R, int32_t K, int32_t L,
                         int32_t S, const double* theta, const double* eta, const double* pr,
                         double* theta_out, double* eta_out, double* pr_out, int32_t flags,
                         void* ws, size_t ws_bytes, void* stream, cudaEvent_t* ev) {
-  MMSBM_REQUIRE(useg && uadj && udeg && iseg && iadj && ideg && theta && eta && pr && theta_out &&
-                    eta_out && pr_out && ws, MMSBM_EINVAL, "mmsbm_em_step: null pointer");
+  MMSBM_REQUIRE(useg && uadj && udeg && iseg && iadj && ideg && usched && isched && theta && eta && pr &&
+                    theta_out && eta_out && pr_out && ws, MMSBM_EINVAL, "mmsbm_em_step: null pointer");
   MMSBM_REQUIRE(N >= 0 && U > 0 && I > 0 && R > 0 && K > 0 && L > 0 && S > 0, MMSBM_EINVAL,
                 "mmsbm_em_step: bad size");
   MMSBM_REQUIRE(K <= 256 && L <= 256 && R <= 31, MMSBM_ERANGE,
                 "mmsbm_em_step: K, L <= 256 and R <= 31 supported (K=%d L=%d R=%d)", K, L, R);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  EmDims d = em_dims(U, I, R, K, L, S);
+  EmDims d = em_dims(N, U, I, R, K, L, S);
   Arena arena(ws, ws_bytes);
   double* pw_u = arena.take<double>(d.p_elems);
   double* pn_u = arena.take<double>(d.p_elems);
@@ -550,7 +584,9 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
   double* wg_u = arena.take<double>(d.wg_u_elems);
   double* wg_i = arena.take<double>(d.wg_i_elems);
   double* partial = arena.take<double>(d.partial_elems);
-  MMSBM_REQUIRE(pw_u && pn_u && pw_i && pn_i && wg_u && wg_i && partial, MMSBM_ENOMEM,
+  double* slots_u = arena.take<double>(d.slots_u_elems);
+  double* slots_i = arena.take<double>(d.slots_i_elems);
+  MMSBM_REQUIRE(pw_u && pn_u && pw_i && pn_i && wg_u && wg_i && partial && slots_u && slots_i, MMSBM_ENOMEM,
                 "mmsbm_em_step: workspace too small (%zu)", ws_bytes);
   int rc;
 #define MMSBM_MARK(k) do { if (ev) MMSBM_CUDA(cudaEventRecord(ev[k], st)); } while (0)
@@ -566,14 +602,14 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
   MMSBM_MARK(1);
   // ---- by-user pass: g of every user (gathers eta rows) ----
   {
-    SegArgs a{useg, uadj, eta, wg_u, U, I, d.ldl, R, 0};
-    if ((rc = launch_segment_pass(a, N, S, st))) return rc;
+    SegArgs a{useg, uadj, usched, eta, wg_u, slots_u, d.pmax_u, d.lmax, U, I, d.ldl, R, 0};
+    if ((rc = launch_segment_pass_and_fixup(a, N, S, st))) return rc;
   }
   MMSBM_MARK(2);
   // ---- by-item pass: g of every item (gathers theta rows) ----
   {
-    SegArgs a{iseg, iadj, theta, wg_i, I, U, d.ldk, R, 0};
-    if ((rc = launch_segment_pass(a, N, S, st))) return rc;
+    SegArgs a{iseg, iadj, isched, theta, wg_i, slots_i, d.pmax_i, d.lmax, I, U, d.ldk, R, 0};
+    if ((rc = launch_segment_pass_and_fixup(a, N, S, st))) return rc;
   }
   MMSBM_MARK(3);
   // ---- theta' and eta' = (g x Pn) o own / max(deg,1) ----
@@ -611,12 +647,13 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
 }
 
 extern "C" int mmsbm_em_step(const int32_t* useg, const int32_t* uadj, const int32_t* udeg,
-                             const int32_t* iseg, const int32_t* iadj, const int32_t* ideg,
+                             const int32_t* iseg, const int32_t* iadj, const int32_t* ideg, const int32_t* usched,
+                 const int32_t* isched,
                              int64_t N, int32_t U, int32_t I, int32_t R, int32_t K, int32_t L,
                              int32_t S, const double* theta, const double* eta, const double* pr,
                              double* theta_out, double* eta_out, double* pr_out, int32_t flags,
                              void* ws, size_t ws_bytes, void* stream) {
-  return em_step_impl(useg, uadj, udeg, iseg, iadj, ideg, N, U, I, R, K, L, S, theta, eta, pr,
+  return em_step_impl(useg, uadj, udeg, iseg, iadj, ideg, usched, isched, N, U, I, R, K, L, S, theta, eta, pr,
                       theta_out, eta_out, pr_out, flags, ws, ws_bytes, stream, nullptr);
 }
 
@@ -624,7 +661,8 @@ extern "C" int mmsbm_em_step(const int32_t* useg, const int32_t* uadj, const int
 // time in ms of {P tables + w GEMMs, by-user pass, by-item pass, n GEMMs, pr accumulate,
 // pr finalize}.
 extern "C" int mmsbm_em_step_profiled(const int32_t* useg, const int32_t* uadj, const int32_t* udeg,
-                                      const int32_t* iseg, const int32_t* iadj, const int32_t* ideg,
+                                      const int32_t* iseg, const int32_t* iadj, const int32_t* ideg, const int32_t* usched,
+                 const int32_t* isched,
                                       int64_t N, int32_t U, int32_t I, int32_t R, int32_t K,
                                       int32_t L, int32_t S, const double* theta, const double* eta,
                                       const double* pr, double* theta_out, double* eta_out,
@@ -633,7 +671,7 @@ extern "C" int mmsbm_em_step_profiled(const int32_t* useg, const int32_t* uadj, 
   MMSBM_REQUIRE(ms6, MMSBM_EINVAL, "mmsbm_em_step_profiled: null output");
   cudaEvent_t ev[7];
   for (int k = 0; k < 7; ++k) MMSBM_CUDA(cudaEventCreate(&ev[k]));
-  int rc = em_step_impl(useg, uadj, udeg, iseg, iadj, ideg, N, U, I, R, K, L, S, theta, eta, pr,
+  int rc = em_step_impl(useg, uadj, udeg, iseg, iadj, ideg, usched, isched, N, U, I, R, K, L, S, theta, eta, pr,
                         theta_out, eta_out, pr_out, flags, ws, ws_bytes, stream, ev);
   if (rc == 0) {
     cudaError_t e = cudaEventSynchronize(ev[6]);
@@ -645,7 +683,8 @@ extern "C" int mmsbm_em_step_profiled(const int32_t* useg, const int32_t* uadj, 
 }
 
 extern "C" int mmsbm_em_run(const int32_t* useg, const int32_t* uadj, const int32_t* udeg,
-                            const int32_t* iseg, const int32_t* iadj, const int32_t* ideg,
+                            const int32_t* iseg, const int32_t* iadj, const int32_t* ideg, const int32_t* usched,
+                 const int32_t* isched,
                             int64_t N, int32_t U, int32_t I, int32_t R, int32_t K, int32_t L,
                             int32_t S, int32_t iterations, double* theta_a, double* eta_a,
                             double* pr_a, double* theta_b, double* eta_b, double* pr_b, void* ws,
@@ -653,7 +692,7 @@ extern "C" int mmsbm_em_run(const int32_t* useg, const int32_t* uadj, const int3
   MMSBM_REQUIRE(iterations >= 0, MMSBM_EINVAL, "mmsbm_em_run: negative iteration count");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto step = [&](bool fwd) {
-    return mmsbm_em_step(useg, uadj, udeg, iseg, iadj, ideg, N, U, I, R, K, L, S,
+    return mmsbm_em_step(useg, uadj, udeg, iseg, iadj, ideg, usched, isched, N, U, I, R, K, L, S,
                          fwd ? theta_a : theta_b, fwd ? eta_a : eta_b, fwd ? pr_a : pr_b,
                          fwd ? theta_b : theta_a, fwd ? eta_b : eta_a, fwd ? pr_b : pr_a, 0, ws,
                          ws_bytes, stream);

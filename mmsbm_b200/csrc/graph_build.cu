@@ -206,13 +206,69 @@ __global__ void degrees_kernel(const int32_t* seg, int n_ids, int R, int32_t* de
 
 __global__ void set_last_kernel(int32_t* seg, int64_t nkeys, int32_t n) { seg[nkeys] = n; }
 
+// ---- work schedule of the segment pass ------------------------------------------------------
+// A segment (all ratings of a user, or of an item) is cut into pieces of at most
+// MMSBM_PIECE_LEN ratings; one warp processes one piece.  Single-piece segments write their g row
+// in place; the pieces of a long segment write partial rows into numbered slots that a fix-up
+// kernel adds up in piece order (deterministic).  This bounds the work of one warp whatever the
+// degree distribution (real rating graphs are heavy-tailed: a handful of items hold 1e5+ ratings).
+// sched layout (int32): [0] pieces P, [1] slots, [2] long segments, [3] piece length,
+//   piece_seg[Pmax] piece_idx[Pmax] piece_slot[Pmax] long_seg[Lmax] long_slot0[Lmax+1]
+__host__ __device__ inline int64_t sched_pmax(int64_t N, int64_t nseg) { return nseg + N / MMSBM_PIECE_LEN + 1; }
+__host__ __device__ inline int64_t sched_lmax(int64_t N) { return N / MMSBM_PIECE_LEN + 1; }
+
+__global__ void sched_count_kernel(const int32_t* deg, int nseg, int32_t* pps, int32_t* nslot, int32_t* nlong) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nseg) return;
+  int p = (deg[t] + MMSBM_PIECE_LEN - 1) / MMSBM_PIECE_LEN;
+  if (p < 1) p = 1;
+  pps[t] = p;
+  nslot[t] = p > 1 ? p : 0;
+  nlong[t] = p > 1 ? 1 : 0;
+}
+
+__global__ void sched_fill_kernel(const int32_t* deg, int nseg, const int32_t* piece_base,
+                                  const int32_t* slot_base, const int32_t* long_base, int64_t pmax,
+                                  int64_t lmax, int32_t* sched) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nseg) return;
+  int32_t* piece_seg = sched + 4;
+  int32_t* piece_idx = piece_seg + pmax;
+  int32_t* piece_slot = piece_idx + pmax;
+  int32_t* long_seg = piece_slot + pmax;
+  int32_t* long_slot0 = long_seg + lmax;
+  int p = (deg[t] + MMSBM_PIECE_LEN - 1) / MMSBM_PIECE_LEN;
+  if (p < 1) p = 1;
+  const int pb = piece_base[t], sb = slot_base[t];
+  for (int k = 0; k < p; ++k) {
+    piece_seg[pb + k] = t;
+    piece_idx[pb + k] = k;
+    piece_slot[pb + k] = p > 1 ? sb + k : -1;
+  }
+  if (p > 1) {
+    long_seg[long_base[t]] = t;
+    long_slot0[long_base[t]] = sb;
+  }
+  if (t == nseg - 1) {                       // totals and the closing slot boundary
+    const int n_slots = sb + (p > 1 ? p : 0);
+    const int n_long = long_base[t] + (p > 1 ? 1 : 0);
+    sched[0] = pb + p;
+    sched[1] = n_slots;
+    sched[2] = n_long;
+    sched[3] = MMSBM_PIECE_LEN;
+    long_slot0[n_long] = n_slots;
+  }
+}
+
 struct GraphWs {
   uint32_t *key_a, *key_b, *val_a, *val_b;
   int32_t *hist, *counts, *tile_sums;
+  int32_t *sa, *sb, *sc;   // schedule scratch: per-segment counts, scanned in place
   int* bad;
 };
 
-static size_t graph_ws_layout(int64_t N, int64_t max_keys, void* base, size_t cap, GraphWs* out) {
+static size_t graph_ws_layout(int64_t N, int64_t max_keys, int64_t max_segs, void* base, size_t cap,
+                              GraphWs* out) {
   const int64_t n_chunks = (N + kChunk - 1) / kChunk;
   const int64_t n_counts = n_chunks * kRadix;
   const int64_t big = n_counts > max_keys + 1 ? n_counts : max_keys + 1;
@@ -221,6 +277,7 @@ static size_t graph_ws_layout(int64_t N, int64_t max_keys, void* base, size_t ca
   auto bump = [&](size_t bytes) { need += align_up(bytes); };
   bump(N * 4); bump(N * 4); bump(N * 4); bump(N * 4);
   bump((max_keys + 1) * 4); bump(n_counts * 4); bump((scan_tiles_for(big) + 1) * 4); bump(256);
+  bump(max_segs * 4); bump(max_segs * 4); bump(max_segs * 4);
   if (base && out) {
     out->key_a = a.take<uint32_t>(N); out->key_b = a.take<uint32_t>(N);
     out->val_a = a.take<uint32_t>(N); out->val_b = a.take<uint32_t>(N);
@@ -228,7 +285,8 @@ static size_t graph_ws_layout(int64_t N, int64_t max_keys, void* base, size_t ca
     out->counts = a.take<int32_t>(n_counts);
     out->tile_sums = a.take<int32_t>(scan_tiles_for(big) + 1);
     out->bad = a.take<int>(64);
-    if (!out->bad) return 0;
+    out->sa = a.take<int32_t>(max_segs); out->sb = a.take<int32_t>(max_segs); out->sc = a.take<int32_t>(max_segs);
+    if (!out->bad || !out->sc) return 0;
   }
   return need;
 }
@@ -274,9 +332,29 @@ static int build_one(const int32_t* id, const int32_t* other, const int32_t* lev
   return 0;
 }
 
+static int build_schedule(const int32_t* deg, int nseg, int64_t N, int32_t* sched, GraphWs& w,
+                          cudaStream_t st) {
+  const unsigned grid = (unsigned)((nseg + 255) / 256);
+  sched_count_kernel<<<grid, 256, 0, st>>>(deg, nseg, w.sa, w.sb, w.sc);
+  MMSBM_LAUNCH_CHECK("sched_count_kernel");
+  int rc;
+  if ((rc = exclusive_scan(w.sa, w.sa, nseg, w.tile_sums, st))) return rc;
+  if ((rc = exclusive_scan(w.sb, w.sb, nseg, w.tile_sums, st))) return rc;
+  if ((rc = exclusive_scan(w.sc, w.sc, nseg, w.tile_sums, st))) return rc;
+  sched_fill_kernel<<<grid, 256, 0, st>>>(deg, nseg, w.sa, w.sb, w.sc, sched_pmax(N, nseg), sched_lmax(N), sched);
+  MMSBM_LAUNCH_CHECK("sched_fill_kernel");
+  return 0;
+}
+
 }  // namespace mmsbm
 
 using namespace mmsbm;
+
+extern "C" int mmsbm_sched_elems(int64_t N, int32_t nseg, int64_t* elems) {
+  MMSBM_REQUIRE(elems && N >= 0 && nseg > 0, MMSBM_EINVAL, "mmsbm_sched_elems: bad argument");
+  *elems = 4 + 3 * sched_pmax(N, nseg) + 2 * sched_lmax(N) + 1;
+  return 0;
+}
 
 extern "C" int mmsbm_graph_workspace_bytes(int64_t N, int32_t U, int32_t I, int32_t R, size_t* bytes) {
   MMSBM_REQUIRE(bytes && N >= 0 && U > 0 && I > 0 && R > 0, MMSBM_EINVAL,
@@ -285,16 +363,17 @@ extern "C" int mmsbm_graph_workspace_bytes(int64_t N, int32_t U, int32_t I, int3
                     (int64_t)I * R < ((int64_t)1 << 31), MMSBM_ERANGE,
                 "index build: N, U*R and I*R must be below 2^31");
   const int64_t mk = (int64_t)(U > I ? U : I) * R;
-  *bytes = graph_ws_layout(N, mk, nullptr, 0, nullptr);
+  *bytes = graph_ws_layout(N, mk, U > I ? U : I, nullptr, 0, nullptr);
   return 0;
 }
 
 extern "C" int mmsbm_graph_build(const int32_t* user, const int32_t* item, const int32_t* level,
                                  int64_t N, int32_t U, int32_t I, int32_t R, int32_t* useg,
                                  int32_t* uadj, int32_t* uperm, int32_t* udeg, int32_t* iseg,
-                                 int32_t* iadj, int32_t* iperm, int32_t* ideg, void* ws,
-                                 size_t ws_bytes, void* stream) {
-  MMSBM_REQUIRE(useg && udeg && iseg && ideg && ws, MMSBM_EINVAL, "mmsbm_graph_build: null pointer");
+                                 int32_t* iadj, int32_t* iperm, int32_t* ideg, int32_t* usched,
+                                 int32_t* isched, void* ws, size_t ws_bytes, void* stream) {
+  MMSBM_REQUIRE(useg && udeg && iseg && ideg && usched && isched && ws, MMSBM_EINVAL,
+                "mmsbm_graph_build: null pointer");
   MMSBM_REQUIRE(N == 0 || (user && item && level && uadj && uperm && iadj && iperm), MMSBM_EINVAL,
                 "mmsbm_graph_build: null pointer");
   size_t need = 0;
@@ -304,10 +383,10 @@ extern "C" int mmsbm_graph_build(const int32_t* user, const int32_t* item, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GraphWs w{};
   const int64_t mk = (int64_t)(U > I ? U : I) * R;
-  graph_ws_layout(N, mk, ws, ws_bytes, &w);
-  MMSBM_REQUIRE(w.bad, MMSBM_ENOMEM, "mmsbm_graph_build: workspace carve-up failed");
-  rc = build_one(user, item, level, N, U, R, useg, uadj, uperm, udeg, w, st);
-  if (rc) return rc;
-  rc = build_one(item, user, level, N, I, R, iseg, iadj, iperm, ideg, w, st);
-  return rc;
+  graph_ws_layout(N, mk, U > I ? U : I, ws, ws_bytes, &w);
+  MMSBM_REQUIRE(w.bad && w.sc, MMSBM_ENOMEM, "mmsbm_graph_build: workspace carve-up failed");
+  if ((rc = build_one(user, item, level, N, U, R, useg, uadj, uperm, udeg, w, st))) return rc;
+  if ((rc = build_schedule(udeg, U, N, usched, w, st))) return rc;
+  if ((rc = build_one(item, user, level, N, I, R, iseg, iadj, iperm, ideg, w, st))) return rc;
+  return build_schedule(ideg, I, N, isched, w, st);
 }

@@ -152,19 +152,22 @@ static int download_rows(Scope& sc, const double* dev, size_t rows, int w, doubl
   return 0;
 }
 
-struct DevGraph { int32_t *useg, *uadj, *uperm, *udeg, *iseg, *iadj, *iperm, *ideg; };
+struct DevGraph { int32_t *useg, *uadj, *uperm, *udeg, *iseg, *iadj, *iperm, *ideg, *usched, *isched; };
 
 static int build_graph(Scope& sc, const DevTriples& t, int64_t N, int U, int I, int R, DevGraph* g) {
   TRY(sc.alloc(&g->useg, (size_t)U * R + 1)); TRY(sc.alloc(&g->uadj, (size_t)N));
   TRY(sc.alloc(&g->uperm, (size_t)N)); TRY(sc.alloc(&g->udeg, (size_t)U));
   TRY(sc.alloc(&g->iseg, (size_t)I * R + 1)); TRY(sc.alloc(&g->iadj, (size_t)N));
   TRY(sc.alloc(&g->iperm, (size_t)N)); TRY(sc.alloc(&g->ideg, (size_t)I));
+  int64_t su = 0, si = 0;
+  TRY(mmsbm_sched_elems(N, U, &su)); TRY(mmsbm_sched_elems(N, I, &si));
+  TRY(sc.alloc(&g->usched, (size_t)su)); TRY(sc.alloc(&g->isched, (size_t)si));
   size_t wsb = 0;
   TRY(mmsbm_graph_workspace_bytes(N, U, I, R, &wsb));
   char* ws;
   TRY(sc.alloc(&ws, wsb));
   return mmsbm_graph_build(t.u, t.i, t.r, N, U, I, R, g->useg, g->uadj, g->uperm, g->udeg, g->iseg,
-                           g->iadj, g->iperm, g->ideg, ws, wsb, sc.st);
+                           g->iadj, g->iperm, g->ideg, g->usched, g->isched, ws, wsb, sc.st);
 }
 
 static int check_common(const void* data, int64_t N, const void* th, int U, int K, const void* et,
@@ -241,9 +244,9 @@ extern "C" int mmsbm_host_update_coefficients(const int64_t* data, int64_t N, co
   MMSBM_CUDA(cudaMemcpyAsync(dpr, pr, (size_t)K * L * R * 8, cudaMemcpyHostToDevice, sc.st));
   TRY(sc.alloc(&oth, (size_t)U * ldk)); TRY(sc.alloc(&oet, (size_t)I * ldl));
   TRY(sc.alloc(&opr, (size_t)K * L * R));
-  size_t wsb = 0; TRY(mmsbm_em_workspace_bytes(U, I, R, K, L, 1, &wsb));
+  size_t wsb = 0; TRY(mmsbm_em_workspace_bytes(N, U, I, R, K, L, 1, &wsb));
   char* ws; TRY(sc.alloc(&ws, wsb));
-  TRY(mmsbm_em_step(g.useg, g.uadj, g.udeg, g.iseg, g.iadj, g.ideg, N, U, I, R, K, L, 1, dth, det, dpr,
+  TRY(mmsbm_em_step(g.useg, g.uadj, g.udeg, g.iseg, g.iadj, g.ideg, g.usched, g.isched, N, U, I, R, K, L, 1, dth, det, dpr,
                     oth, oet, opr, MMSBM_RAW_THETA | MMSBM_RAW_ETA_PR, ws, wsb, sc.st));
   TRY(download_rows(sc, oth, (size_t)U, K, n_theta));
   TRY(download_rows(sc, oet, (size_t)I, L, n_eta));
@@ -316,12 +319,12 @@ extern "C" int mmsbm_host_fit(const int64_t* data, int64_t N, int32_t U, int32_t
   TRY(sc.alloc(&thb, (size_t)S * U * ldk)); TRY(sc.alloc(&etb, (size_t)S * I * ldl));
   TRY(sc.alloc(&prb, prn)); TRY(sc.alloc(&dlik, (size_t)S));
   size_t wsb = 0, lwsb = 0;
-  TRY(mmsbm_em_workspace_bytes(U, I, R, K, L, S, &wsb));
+  TRY(mmsbm_em_workspace_bytes(N, U, I, R, K, L, S, &wsb));
   TRY(mmsbm_likelihood_workspace_bytes(U, S, &lwsb));
   char *ws, *lws;
   TRY(sc.alloc(&ws, wsb)); TRY(sc.alloc(&lws, lwsb));
   tr.mark("params H2D + alloc");
-  TRY(mmsbm_em_run(g.useg, g.uadj, g.udeg, g.iseg, g.iadj, g.ideg, N, U, I, R, K, L, S, iterations, tha,
+  TRY(mmsbm_em_run(g.useg, g.uadj, g.udeg, g.iseg, g.iadj, g.ideg, g.usched, g.isched, N, U, I, R, K, L, S, iterations, tha,
                    eta_a, pra, thb, etb, prb, ws, wsb, sc.st));
   tr.mark("EM iterations");
   const bool in_a = (iterations % 2) == 0;

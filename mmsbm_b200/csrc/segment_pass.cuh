@@ -64,8 +64,11 @@ __device__ __forceinline__ double rcp_clamped(double x) {
 struct SegArgs {
   const int32_t* seg;   // [nseg*R+1]
   const int32_t* adj;   // [N] neighbour ids, grouped by (segment, level)
+  const int32_t* sched; // work schedule: pieces of <= MMSBM_PIECE_LEN ratings (graph_build.cu)
   const double* nbr;    // [S][nnbr][NBp]
-  double* wg;           // [S][nseg][R*NBp]  in: w   out: g (in place)
+  double* wg;           // [S][nseg][R*NBp]  in: w   out: g (in place; single-piece segments)
+  double* partial;      // [S][lmax][R*NBp]  out: g of the pieces of long segments, by slot
+  int64_t pmax, lmax;   // capacities of the schedule arrays
   int nseg, nnbr, NBp, R, segs_per_cta;
 };
 
@@ -138,10 +141,16 @@ segment_pass_kernel(const SegArgs A) {
 
   const int grp = lane / G, q = lane - grp * G;
   const bool lane_on = grp < RPS;                // lanes past RPS*G idle (32 % G of them)
+  // this CTA's range of pieces (a piece = up to MMSBM_PIECE_LEN ratings of one segment)
+  const int32_t* piece_seg = A.sched + 4;
+  const int32_t* piece_idx = piece_seg + A.pmax;
+  const int32_t* piece_slot = piece_idx + A.pmax;
+  const int n_pieces = __ldg(A.sched);
   const int seg_lo = blockIdx.x * A.segs_per_cta;
-  const int seg_hi = min(seg_lo + A.segs_per_cta, A.nseg);
+  const int seg_hi = min(seg_lo + A.segs_per_cta, n_pieces);
   const double* nbr_run = A.nbr + (size_t)run * A.nnbr * NBp;
   double* wg_run = A.wg + (size_t)run * A.nseg * RNB;
+  double* part_run = A.partial + (size_t)run * A.lmax * RNB;
   int coff[CH];                                  // lane-constant chunk offsets (in doubles)
   bool con[CH];
 #pragma unroll
@@ -159,33 +168,38 @@ segment_pass_kernel(const SegArgs A) {
     for (int p = lane; p < (RNB >> 1); p += 32) cp_async16(dst + 2 * p, src + 2 * p);
   };
 
-  int sg = seg_lo + warp, buf = 0;
-  int bend_pref = 0;                             // lane r <= R holds the start of level r
-  if (sg < seg_hi) {
-    if (lane <= R) bend_pref = __ldg(A.seg + (size_t)sg * R + lane);
-    fetch_w(sg, 0);
-  }
+  // prefetched state of a piece: its segment, (piece number, slot) in lanes 0 and 1, and the
+  // level boundaries of the segment (lane r <= R holds the start of level r)
+  int pi = seg_lo + warp, buf = 0;
+  int sg = 0, pinfo_pref = 0, bend_pref = 0;
+  auto prefetch_piece = [&](int p_, int b_, int& sg_out) {
+    sg_out = __ldg(piece_seg + p_);
+    pinfo_pref = (lane == 0) ? __ldg(piece_idx + p_) : (lane == 1) ? __ldg(piece_slot + p_) : 0;
+    if (lane <= R) bend_pref = __ldg(A.seg + (size_t)sg_out * R + lane);
+    fetch_w(sg_out, b_);
+  };
+  if (pi < seg_hi) prefetch_piece(pi, 0, sg);
   cp_async_commit();
 
-  while (sg < seg_hi) {
-    const int bend_reg = bend_pref;
-    // claim the next segment, start fetching its boundaries and its w row
+  while (pi < seg_hi) {
+    const int bend_reg = bend_pref, pinfo = pinfo_pref;
+    // claim the next piece, start fetching its descriptors and its w row
     int t = 0;
     if (lane == 0) t = atomicAdd(ctr, 1);
-    const int sg_next = seg_lo + __shfl_sync(kFull, t, 0);
-    if (sg_next < seg_hi) {
-      if (lane <= R) bend_pref = __ldg(A.seg + (size_t)sg_next * R + lane);
-      fetch_w(sg_next, buf ^ 1);
-    }
+    const int pi_next = seg_lo + __shfl_sync(kFull, t, 0);
+    int sg_next = 0;
+    if (pi_next < seg_hi) prefetch_piece(pi_next, buf ^ 1, sg_next);
     cp_async_commit();
-    const int beg = __shfl_sync(kFull, bend_reg, 0), end = __shfl_sync(kFull, bend_reg, R);
+    const int slot = __shfl_sync(kFull, pinfo, 1);
+    const int beg = __shfl_sync(kFull, bend_reg, 0) + __shfl_sync(kFull, pinfo, 0) * MMSBM_PIECE_LEN;
+    const int end = min(beg + MMSBM_PIECE_LEN, __shfl_sync(kFull, bend_reg, R));
     // ids of the first chunk; slots past the end read row 0 (in bounds, weight zero)
     int cur_ids = 0;
     if (lane < SLOTS && beg + lane < end) cur_ids = ld_stream(A.adj + beg + lane);
     cp_async_wait<1>();                          // this segment's w has landed
     __syncwarp();
     const double* wb = wbuf + (size_t)buf * RNB;
-    double* gout = wg_run + (size_t)sg * RNB;
+    double* gout = (slot < 0) ? wg_run + (size_t)sg * RNB : part_run + (size_t)slot * RNB;
 
     int cur_r = 0;                               // level the accumulators g belong to
     int lvl = 0, nb = __shfl_sync(kFull, bend_reg, 1);   // level of the chunk's first row, its end
@@ -310,6 +324,7 @@ segment_pass_kernel(const SegArgs A) {
     __syncwarp();
     buf ^= 1;
     sg = sg_next;
+    pi = pi_next;
   }
   cp_async_wait<0>();
 }

@@ -65,6 +65,10 @@ class Engine:
             self._empty(U * R + 1, i32), self._empty(N, i32), self._empty(N, i32), self._empty(U, i32))
         self.iseg, self.iadj, self.iperm, self.ideg = (
             self._empty(I * R + 1, i32), self._empty(N, i32), self._empty(N, i32), self._empty(I, i32))
+        n_u, n_i = _lib.C.c_int64(0), _lib.C.c_int64(0)
+        _lib.check(self.lib.mmsbm_sched_elems(N, U, _lib.C.byref(n_u)), "sched_elems")
+        _lib.check(self.lib.mmsbm_sched_elems(N, I, _lib.C.byref(n_i)), "sched_elems")
+        self.usched, self.isched = self._empty(n_u.value, i32), self._empty(n_i.value, i32)
         need = _lib.C.c_size_t(0)
         _lib.check(self.lib.mmsbm_graph_workspace_bytes(N, U, I, R, _lib.C.byref(need)), "graph_workspace_bytes")
         ws = self._bytes(need.value)
@@ -72,13 +76,15 @@ class Engine:
             self.cols[0].data_ptr(), self.cols[1].data_ptr(), self.cols[2].data_ptr(), N, U, I, R,
             self.useg.data_ptr(), self.uadj.data_ptr(), self.uperm.data_ptr(), self.udeg.data_ptr(),
             self.iseg.data_ptr(), self.iadj.data_ptr(), self.iperm.data_ptr(), self.ideg.data_ptr(),
+            self.usched.data_ptr(), self.isched.data_ptr(),
             ws.data_ptr(), need.value, self._stream()), "graph_build")
         torch.cuda.current_stream(self.device).synchronize()   # ws is released on return
         del ws
 
     def _graph_args(self):
         return (self.useg.data_ptr(), self.uadj.data_ptr(), self.udeg.data_ptr(),
-                self.iseg.data_ptr(), self.iadj.data_ptr(), self.ideg.data_ptr())
+                self.iseg.data_ptr(), self.iadj.data_ptr(), self.ideg.data_ptr(),
+                self.usched.data_ptr(), self.isched.data_ptr())
 
     # ---------------------------------------------------------------- parameters
     def _pad(self, x, ld):
@@ -105,7 +111,7 @@ class Engine:
         self.pr = torch.from_numpy(np.ascontiguousarray(pr, dtype=np.float64)).to(dev)
         self._alt = (torch.empty_like(self.theta), torch.empty_like(self.eta), torch.empty_like(self.pr))
         need = _lib.C.c_size_t(0)
-        _lib.check(self.lib.mmsbm_em_workspace_bytes(self.U, self.I, self.R, self.K, self.L, S,
+        _lib.check(self.lib.mmsbm_em_workspace_bytes(self.N, self.U, self.I, self.R, self.K, self.L, S,
                                                      _lib.C.byref(need)), "em_workspace_bytes")
         self._ws = self._bytes(need.value)
         self._ws_bytes = need.value
