@@ -246,28 +246,60 @@ class MMSBM:
         return {"stats": stats, "objects": {"theta": self.theta, "eta": self.eta, "pr": self.pr}}
 
     # ----------------------------------------------------------------------- cv_fit
-    def cv_fit(self, data, folds=5):
-        """k-fold cross-validation; returns the accuracy of every fold and keeps the
-        objects of the most accurate one (src/mmsbm.py:371-472)."""
+    def _make_folds(self, data, folds):
+        """(train, test) DataFrames of every fold, built as the reference does
+        (src/mmsbm.py:415-439): per user (groups in sorted key order) up to items_per_fold
+        held-out rows, drawn from ``self.rng`` in that order; index label 0 is never held out
+        (the reference filters str(a) != "0", :435).  The fits do not touch ``self.rng``, so
+        building all folds first consumes it exactly as the reference's interleaved loop."""
         items_per_fold = structure_folds(data, folds)
         temp = data
-        all_results = []
-        for f in range(folds):
-            self.logger.info(f"Running fold {f + 1} of {folds}...")
-            # per user (groups in sorted key order), up to items_per_fold held-out rows;
-            # draws come from self.rng in that order.  Index label 0 is never held out
-            # (the reference filters str(a) != "0", src/mmsbm.py:435).
+        pairs = []
+        for _ in range(folds):
             picked = []
             for _, group in temp.groupby(temp.columns[0]):
                 chosen = get_n_per_group(group, n=items_per_fold, rng=self.rng)
                 picked.extend(chosen)
             test_indices = [a for a in picked if str(a) != "0"]
-
             test = temp.loc[test_indices, :]
             train = data[~data.index.isin(test.index)]
             temp = temp[~temp.index.isin(test_indices)]
+            pairs.append((train, test))
+        return pairs
 
-            self.fit(train, silent=True)
+    def cv_fit(self, data, folds=5):
+        """k-fold cross-validation; returns the accuracy of every fold and keeps the objects of
+        the most accurate one (src/mmsbm.py:371-472).  Under torch.distributed the folds x runs
+        jobs shard over the ranks; the result is the same."""
+        pairs = self._make_folds(data, folds)
+        rank, world = dist_info()
+        shard_jobs = world > 1 and self.shard == "runs"
+        done = {}
+        if shard_jobs:
+            jobs = [(f, s) for f in range(folds) for s in range(self.sampling)]
+            mine = jobs[rank::world]
+            local = {}
+            for f in sorted({f for f, _ in mine}):
+                self.data_handler = DataHandler()
+                self._prepare_objects(self.data_handler.format_train_data(pairs[f][0]))
+                runs = [s for (ff, s) in mine if ff == f]
+                out = self._run_batch(self._engine, [self.child_states[s] for s in runs], runs)
+                local.update({(f, s): out[s] for s in runs})
+            import torch.distributed as dist
+            boxes = [None] * world
+            dist.all_gather_object(boxes, local)
+            for b in boxes:
+                done.update(b)
+
+        all_results = []
+        for f, (train, test) in enumerate(pairs):
+            self.logger.info(f"Running fold {f + 1} of {folds}...")
+            if shard_jobs:
+                self.data_handler = DataHandler()
+                self._prepare_objects(self.data_handler.format_train_data(train))
+                self.results = [done[(f, s)] for s in range(self.sampling)]
+            else:
+                self.fit(train, silent=True)
             self.prediction_matrix = self.predict(test)
             results = self.score(silent=True)
             all_results.append({

@@ -131,6 +131,34 @@ __global__ void __launch_bounds__(256) k_lane(const double* __restrict__ table, 
   out[1 + t0] = acc;
 }
 
+
+// (E) G lanes per row, ONE 256-bit load per lane (rows of 4*G doubles): the em kernel's layout
+template <int G, int UN>
+__global__ void __launch_bounds__(256) k_group256(const double* __restrict__ table, const int* __restrict__ idx, long n,
+                                                  double* out) {
+  const int lane = threadIdx.x & 31;
+  constexpr int RPS = 32 / G, RD = 4 * G;
+  const int grp = lane / G, q = lane % G;
+  const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long)gridDim.x * blockDim.x) >> 5;
+  const long per = (long)UN * RPS, chunks = n / per;
+  double acc = 0.0;
+  for (long c = gw; c < chunks; c += nw) {
+    int my = (lane < per) ? idx[c * per + lane] : 0;
+    double v[UN][4];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      int id = __shfl_sync(0xffffffffu, my, (u * RPS + grp) & 31);
+      const double* p = table + (size_t)id * RD + 4 * (grp < RPS ? q : 0);
+      ld256(p, v[u][0], v[u][1], v[u][2], v[u][3]);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc = fma(v[u][k], 1.0000001, acc);
+  }
+  out[1 + blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
 
 template <typename F>
@@ -171,6 +199,14 @@ int main(int argc, char** argv) {
   timeit("B ldg128 G=10 UN=8", n, [&] { k_group<10, 8><<<148 * 8, 256>>>(table, idx, n, out); });
   timeit("B ldg128 G=5  UN=4", n, [&] { k_group<5, 4><<<148 * 8, 256>>>(table, idx, n, out); });
   timeit("B ldg128 G=2  UN=2", n, [&] { k_group<2, 2><<<148 * 8, 256>>>(table, idx, n, out); });
+  {
+    // same number of BYTES gathered: 160-byte rows with 5 lanes vs 320-byte rows with 10 lanes
+    double* t2; CK(cudaMalloc(&t2, nrows * 320)); CK(cudaMemset(t2, 0, nrows * 320));
+    timeit("E ld256 G=5 160B rows UN=2", n, [&] { k_group256<5, 2><<<148 * 12, 256>>>(table, idx, n, out); });
+    timeit("E ld256 G=5 160B rows UN=4", n, [&] { k_group256<5, 4><<<148 * 8, 256>>>(table, idx, n, out); });
+    timeit("E ld256 G=10 320B rows UN=4 (n/2 rows)", n / 2, [&] { k_group256<10, 4><<<148 * 12, 256>>>(t2, idx, n / 2, out); });
+    timeit("E ld256 G=10 320B rows UN=8 (n/2 rows)", n / 2, [&] { k_group256<10, 8><<<148 * 8, 256>>>(t2, idx, n / 2, out); });
+  }
   timeit("C ld256 lane/row", n, [&] { k_lane<true><<<148 * 8, 256>>>(table, idx, n, out); });
   timeit("D ld128 lane/row", n, [&] { k_lane<false><<<148 * 8, 256>>>(table, idx, n, out); });
   return 0;

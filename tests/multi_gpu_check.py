@@ -54,6 +54,21 @@ def main():
     assert worst < 1e-9, worst
     pa, pb = a.predict(df.iloc[:500]), b.predict(df.iloc[:500])
     assert rel_err(pb, pa) < 1e-9
+    # 3. cv_fit: folds x runs jobs sharded over the ranks == serial folds in one process
+    from tests.util import mock_data
+    solo_cv = MMSBM(2, 2, iterations=10, sampling=3, seed=1)
+    folds_pairs = solo_cv._make_folds(mock_data(1), 2)
+    want_acc = []
+    for tr, te in folds_pairs:                    # no process group use: _run_batch directly
+        solo_cv.data_handler = __import__("mmsbm_b200").DataHandler()
+        solo_cv._prepare_objects(solo_cv.data_handler.format_train_data(tr))
+        r = solo_cv._run_batch(solo_cv._engine, list(solo_cv.child_states), [0, 1, 2])
+        solo_cv.results = [r[0], r[1], r[2]]
+        solo_cv.predict(te)
+        want_acc.append(float(solo_cv.score(silent=True)["stats"]["accuracy"]))
+    c = MMSBM(2, 2, iterations=10, sampling=3, seed=1)
+    got_acc = [float(a) for a in c.cv_fit(mock_data(1), folds=2)]
+    assert got_acc == want_acc, (got_acc, want_acc)
     dist.barrier()
     if rank == 0:
         print(f"multi-gpu ok: world={dist.get_world_size()} rating-sharded worst rel err {worst:.2e}")
