@@ -259,6 +259,48 @@ def run_b200_arm(args, shape):
     build_ms = (time.perf_counter() - t0) * 1e3
     eng.set_params(th0, et0, pr0)
 
+    if args.shard == "ratings" and world > 1:
+        # ONE set of S runs, ratings split by user range over the ranks, n_eta / n_pr all-reduced
+        # over NCCL every iteration (BASELINE.json configs[4]); strong scaling, no e2e / roofline
+        from mmsbm_b200.parallel import RatingShardedEngine
+        del eng
+        seeds0 = np.random.default_rng(1).bit_generator._seed_seq.spawn(S)
+        th0, et0, pr0 = seeded_inits(data, U, I, K, L, seeds0)
+        sh = RatingShardedEngine(data, U, I, R, K, L)
+        sh.set_params(th0, et0, pr0)
+        for _ in range(args.warmup):
+            sh.run(T)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        clocks = ClockSampler(local_rank)
+        launches0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            sh.run(T)
+        e1.record()
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        clk = clocks.stop()
+        lik = sh.likelihood()
+        if rank == 0:
+            print(json.dumps({
+                "metric": "rating-updates/sec", "value": float(N) * T * S * args.steps / (ms * 1e-3),
+                "unit": "rating-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "users": U, "items": I, "ratings": N, "K": K, "L": L,
+                           "R": R, "sampling": S, "iterations_per_step": T, "ids": f"{args.ids}, seed 0",
+                           "parallelism": f"ratings sharded by user range over {world} GPUs, NCCL all-reduce "
+                                          "of n_eta and n_pr every iteration",
+                           "local_ratings": int(sh.engine.N)},
+                "roofline": None, "cpu_baseline": None, "e2e": None,
+                "gpu_launches": int(_lib.launch_count() - launches0), "clocks": clk,
+                "ms_per_iteration": ms / args.steps / T, "likelihood_run0": float(lik[0])}), flush=True)
+        dist.destroy_process_group()
+        return
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
@@ -387,6 +429,9 @@ def main():
     ap.add_argument("--iters-per-step", type=int, default=400)
     ap.add_argument("--cpu-rows", type=int, default=200_000)
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
+    ap.add_argument("--shard", default="runs", choices=["runs", "ratings"],
+                    help="N > 1 only: shard independent runs (default, weak scaling) or the ratings of "
+                         "every run by user range with a per-iteration all-reduce (strong scaling)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -116,7 +116,8 @@ class RatingShardedEngine:
         e = self.engine
         for _ in range(int(iterations)):
             _, eta_raw, pr_raw = e.step_raw(self._lib.RAW_ETA_PR)   # theta' is final: users are owned
-            allreduce_sum_([eta_raw, pr_raw])
+            if self.world > 1:      # n_eta and n_pr share one buffer: a single collective, in place
+                dist.all_reduce(e._alt_flat, op=dist.ReduceOp.SUM)
             e.finalize(eta_raw, pr_raw, ideg=self.ideg)
             e.swap()
 
