@@ -400,7 +400,7 @@ static PassShape choose_shape(int NBp, double avg_degree) {
     if ((NCH + c - 1) / c <= 8) { CH = c; break; }
   }
   const int G = (NCH + CH - 1) / CH;
-  PassShape sh{G, CH, 1, 1};
+  PassShape sh{G, CH, 1, 1};   // CH == 1 implies NBp == 4*G (the kernel relies on it)
   if (CH == 1) { sh.UN = (G == 1) ? 1 : 2; sh.MINB = 3; }
   // short segments are latency bound: one step in flight but 4 CTAs/SM wins there (G = 5 only)
   if (CH == 1 && G == 5 && avg_degree < 256.0) { sh.UN = 1; sh.MINB = 4; }

@@ -131,7 +131,8 @@ segment_pass_kernel(const SegArgs A) {
   extern __shared__ __align__(32) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int run = blockIdx.y;
-  const int R = A.R, NBp = A.NBp, RNB = R * NBp;
+  // one chunk per lane means the row stride is exactly 4*G doubles: a compile-time constant
+  const int R = A.R, NBp = (CH == 1) ? 4 * G : A.NBp, RNB = R * NBp;
   const int NCH = NBp >> 2;                      // 32-byte chunks per neighbour row
 
   double* wbuf = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 2 * RNB;   // [2][RNB]
