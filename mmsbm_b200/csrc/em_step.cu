@@ -16,15 +16,17 @@
 //
 // Kernels of one iteration (all runs in grid.y, run-major so one run's tables stay in L2):
 //   prep_p_kernel        P in the two operand layouts of each side
-//   small_gemm_kernel    [1] for every user and item: W = own x Pw   (register-blocked fp64 FMA)
-//   segment_pass_kernel  [2] THE HOT KERNEL: one warp per segment streams its ratings;
-//                        per rating it moves one neighbour row (8*NB bytes, one 256-bit load
-//                        per lane of a group of G lanes) and 4 bytes of index.  S_n is a
-//                        3-level shuffle reduction over the group, g_r stays in registers and
-//                        is reduced across groups once per (segment, rating level); rows are
-//                        stored grouped by level (include/mmsbm_b200.h).  w comes from W via
-//                        cp.async (prefetched one segment ahead), g overwrites W in place.
-//   small_gemm_kernel    [3] n_own = (G x Pn) o own / max(deg,1)   (normalisation fused)
+//   row_w_kernel         [1] for every user and item: W = own x Pw.  A lane owns a row, P sits in
+//                        shared memory and every read of it is a warp broadcast
+//                        (small_gemm_kernel: tiled fallback for row strides > 32 doubles)
+//   segment_pass_kernel  [2] THE HOT KERNEL (segment_pass.cuh): one warp per piece of a segment
+//                        streams its ratings; per rating it moves one neighbour row (8*NB bytes,
+//                        one 256-bit load per lane of a group of G lanes) and 4 bytes of index.
+//                        w comes from W via cp.async (prefetched one piece ahead), g overwrites W
+//                        in place.  Segments longer than MMSBM_PIECE_LEN ratings are cut into
+//                        pieces by the work schedule built with the index (graph_build.cu); their
+//                        partial g rows are added in piece order by segment_fixup_kernel
+//   row_n_kernel         [3] n_own = (G x Pn) o own / max(deg,1)   (normalisation fused)
 //   pr_accumulate_kernel [4] block-private register accumulators over a slab of segments
 //   pr_finalize_kernel   fixed-order reduce over slabs, x P, normalise over ratings
 // No atomics on data, every sum has a fixed order: results are bit-reproducible.

@@ -80,6 +80,7 @@ class Engine:
             ws.data_ptr(), need.value, self._stream()), "graph_build")
         torch.cuda.current_stream(self.device).synchronize()   # ws is released on return
         del ws
+        self.cols = None            # the int32 columns are only an input of the build
 
     def _graph_args(self):
         return (self.useg.data_ptr(), self.uadj.data_ptr(), self.udeg.data_ptr(),
