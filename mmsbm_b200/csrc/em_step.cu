@@ -564,12 +564,21 @@ extern "C" int mmsbm_em_workspace_bytes(int64_t N, int32_t U, int32_t I, int32_t
   return 0;
 }
 
+// Optional second stream for the kernels that are off the critical path of an iteration
+// (w of the items, both n contractions): they are HBM-streaming while the segment passes are
+// bound by the L1/LSU pipe, so they overlap well.  Created per mmsbm_em_run call.
+struct Overlap {
+  cudaStream_t side = nullptr;
+  cudaEvent_t e[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
 static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t* udeg,
                         const int32_t* iseg, const int32_t* iadj, const int32_t* ideg,
                         const int32_t* usched, const int32_t* isched, int64_t N, int32_t U, int32_t I, int32_t R, int32_t K, int32_t L,
                         int32_t S, const double* theta, const double* eta, const double* pr,
                         double* theta_out, double* eta_out, double* pr_out, int32_t flags,
-                        void* ws, size_t ws_bytes, void* stream, cudaEvent_t* ev) {
+                        void* ws, size_t ws_bytes, void* stream, cudaEvent_t* ev,
+                        const Overlap* ov = nullptr) {
   MMSBM_REQUIRE(useg && uadj && udeg && iseg && iadj && ideg && usched && isched && theta && eta && pr &&
                     theta_out && eta_out && pr_out && ws, MMSBM_EINVAL, "mmsbm_em_step: null pointer");
   MMSBM_REQUIRE(N >= 0 && U > 0 && I > 0 && R > 0 && K > 0 && L > 0 && S > 0, MMSBM_EINVAL,
@@ -593,13 +602,21 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
   int rc;
 #define MMSBM_MARK(k) do { if (ev) MMSBM_CUDA(cudaEventRecord(ev[k], st)); } while (0)
   MMSBM_MARK(0);
+  cudaStream_t s2 = ov ? ov->side : st;        // stream of the off-critical-path kernels
+#define MMSBM_FORK(k) do { if (ov) { MMSBM_CUDA(cudaEventRecord(ov->e[k], st)); \
+                                     MMSBM_CUDA(cudaStreamWaitEvent(s2, ov->e[k], 0)); } } while (0)
+#define MMSBM_JOIN(k) do { if (ov) { MMSBM_CUDA(cudaEventRecord(ov->e[k], s2)); \
+                                     MMSBM_CUDA(cudaStreamWaitEvent(st, ov->e[k], 0)); } } while (0)
+#define MMSBM_SIDE_DONE(k) do { if (ov) MMSBM_CUDA(cudaEventRecord(ov->e[k], s2)); } while (0)
   // ---- P tables and w = own x Pw for every user and item ----
   {
     const int total = d.ldk * d.ldl * R;
     prep_p_kernel<<<dim3((total + 255) / 256, S), 256, 0, st>>>(pr, K, L, R, d.ldk, d.ldl, pw_u, pn_u, pw_i, pn_i);
     MMSBM_LAUNCH_CHECK("prep_p_kernel");
+    MMSBM_FORK(0);                                                  // side: after the P tables
     if ((rc = launch_w(theta, pw_u, wg_u, U, d.ldk, d.rnb_u, S, st))) return rc;
-    if ((rc = launch_w(eta, pw_i, wg_i, I, d.ldl, d.rnb_i, S, st))) return rc;
+    if ((rc = launch_w(eta, pw_i, wg_i, I, d.ldl, d.rnb_i, S, s2))) return rc;
+    MMSBM_SIDE_DONE(1);                                             // w of the items ready
   }
   MMSBM_MARK(1);
   // ---- by-user pass: g of every user (gathers eta rows) ----
@@ -608,19 +625,23 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
     if ((rc = launch_segment_pass_and_fixup(a, N, S, st))) return rc;
   }
   MMSBM_MARK(2);
+  // theta' = (g x Pn) o theta / max(deg,1): off the critical path, overlaps the by-item pass
+  MMSBM_FORK(2);
+  if ((rc = launch_n(wg_u, pn_u, theta, udeg, theta_out, U, d.ldk, d.rnb_u,
+                     (flags & MMSBM_RAW_THETA) ? 0 : 1, S, s2))) return rc;
+  MMSBM_SIDE_DONE(4);
   // ---- by-item pass: g of every item (gathers theta rows) ----
+  if (ov) MMSBM_CUDA(cudaStreamWaitEvent(st, ov->e[1], 0));
   {
     SegArgs a{iseg, iadj, isched, theta, wg_i, slots_i, d.pmax_i, d.lmax, I, U, d.ldk, R, 0};
     if ((rc = launch_segment_pass_and_fixup(a, N, S, st))) return rc;
   }
   MMSBM_MARK(3);
-  // ---- theta' and eta' = (g x Pn) o own / max(deg,1) ----
-  {
-    if ((rc = launch_n(wg_u, pn_u, theta, udeg, theta_out, U, d.ldk, d.rnb_u,
-                       (flags & MMSBM_RAW_THETA) ? 0 : 1, S, st))) return rc;
-    if ((rc = launch_n(wg_i, pn_i, eta, ideg, eta_out, I, d.ldl, d.rnb_i,
-                       (flags & MMSBM_RAW_ETA_PR) ? 0 : 1, S, st))) return rc;
-  }
+  // eta' likewise; overlaps the pr kernels
+  MMSBM_FORK(3);
+  if ((rc = launch_n(wg_i, pn_i, eta, ideg, eta_out, I, d.ldl, d.rnb_i,
+                     (flags & MMSBM_RAW_ETA_PR) ? 0 : 1, S, s2))) return rc;
+  MMSBM_SIDE_DONE(5);
   MMSBM_MARK(4);
   // ---- pr' ----
   PrArgs pa{};
@@ -644,7 +665,14 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
   pr_finalize_kernel<<<dim3((K * L + 127) / 128, S), 128, 0, st>>>(fa);
   MMSBM_LAUNCH_CHECK("pr_finalize_kernel");
   MMSBM_MARK(6);
+  if (ov) {                                                         // join: theta' and eta' are ready
+    MMSBM_CUDA(cudaStreamWaitEvent(st, ov->e[4], 0));
+    MMSBM_CUDA(cudaStreamWaitEvent(st, ov->e[5], 0));
+  }
 #undef MMSBM_MARK
+#undef MMSBM_FORK
+#undef MMSBM_JOIN
+#undef MMSBM_SIDE_DONE
   return 0;
 }
 
@@ -693,18 +721,32 @@ extern "C" int mmsbm_em_run(const int32_t* useg, const int32_t* uadj, const int3
                             size_t ws_bytes, void* stream) {
   MMSBM_REQUIRE(iterations >= 0, MMSBM_EINVAL, "mmsbm_em_run: negative iteration count");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Overlap ov;
+  const bool small = (double)N * S < 5.0e7;
+  const bool overlap = (!small || getenv("MMSBM_FORCE_OVERLAP") != nullptr) && iterations > 0 &&
+                       getenv("MMSBM_NO_OVERLAP") == nullptr;
+  if (overlap) {
+    MMSBM_CUDA(cudaStreamCreateWithFlags(&ov.side, cudaStreamNonBlocking));
+    for (auto& e : ov.e) MMSBM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   auto step = [&](bool fwd) {
-    return mmsbm_em_step(useg, uadj, udeg, iseg, iadj, ideg, usched, isched, N, U, I, R, K, L, S,
-                         fwd ? theta_a : theta_b, fwd ? eta_a : eta_b, fwd ? pr_a : pr_b,
-                         fwd ? theta_b : theta_a, fwd ? eta_b : eta_a, fwd ? pr_b : pr_a, 0, ws,
-                         ws_bytes, stream);
+    return em_step_impl(useg, uadj, udeg, iseg, iadj, ideg, usched, isched, N, U, I, R, K, L, S,
+                        fwd ? theta_a : theta_b, fwd ? eta_a : eta_b, fwd ? pr_a : pr_b,
+                        fwd ? theta_b : theta_a, fwd ? eta_b : eta_a, fwd ? pr_b : pr_a, 0, ws,
+                        ws_bytes, stream, nullptr, overlap ? &ov : nullptr);
   };
+  struct Cleanup {                              // the side stream drains on its own; handles are
+    Overlap& o;                                 // released once their work has completed
+    ~Cleanup() {
+      for (auto& e : o.e) if (e) cudaEventDestroy(e);
+      if (o.side) cudaStreamDestroy(o.side);
+    }
+  } cleanup{ov};
   int done = 0;
   // Launch-bound sizes (a few 10 us of kernels per iteration): capture one a->b->a pair of
   // iterations into a CUDA graph and replay it; the graph lives only inside this call.
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  const bool small = (double)N * S < 5.0e7 && getenv("MMSBM_NO_GRAPH") == nullptr;
-  if (small && iterations >= 8 && st != nullptr && cudaStreamIsCapturing(st, &cap) == cudaSuccess &&
+  if (small && !overlap && getenv("MMSBM_NO_GRAPH") == nullptr && iterations >= 8 && st != nullptr && cudaStreamIsCapturing(st, &cap) == cudaSuccess &&
       cap == cudaStreamCaptureStatusNone) {
     int rc = step(true);                       // first pair uncaptured: sets function attributes
     if (rc == 0) rc = step(false);

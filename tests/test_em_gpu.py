@@ -266,6 +266,30 @@ def test_reproducible_bits():
         np.testing.assert_array_equal(a, b)
 
 
+def test_launch_strategies_give_identical_bits(monkeypatch):
+    """mmsbm_em_run has three launch strategies -- plain launches, CUDA-graph replay of iteration
+    pairs (small problems) and a second stream for the off-critical-path kernels (large ones).
+    They run the same kernels on the same data, so the results must be bit-identical."""
+    from mmsbm_b200.engine import Engine
+    data = random_triples(83, 80000, 900, 500, 5, heavy_tail=True)
+    theta, eta, pr = random_params(89, 900, 500, 12, 9, 5, S=3)
+    outs = {}
+    for name, env in (("plain", {"MMSBM_NO_GRAPH": "1", "MMSBM_NO_OVERLAP": "1"}),
+                      ("graph", {"MMSBM_NO_OVERLAP": "1"}),
+                      ("overlap", {"MMSBM_FORCE_OVERLAP": "1"})):
+        for k in ("MMSBM_NO_GRAPH", "MMSBM_NO_OVERLAP", "MMSBM_FORCE_OVERLAP"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        e = Engine(data, 900, 500, 5, 12, 9)
+        e.set_params(theta, eta, pr)
+        e.run(11)
+        outs[name] = e.get_params() + (e.likelihood(),)
+    for name in ("graph", "overlap"):
+        for a, b in zip(outs["plain"], outs[name]):
+            np.testing.assert_array_equal(a, b, err_msg=name)
+
+
 # ------------------------------------------------------------------- predict / stats (a6, a10)
 def test_predict_stats_vs_oracle():
     from mmsbm_b200.engine import predict_stats
