@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmsbm_b200.so")
+LIB_PATH = os.environ.get("MMSBM_B200_LIB") or os.path.join(_HERE, "libmmsbm_b200.so")
 
 RAW_THETA = 1
 RAW_ETA_PR = 2

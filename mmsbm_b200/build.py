@@ -32,18 +32,22 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
-    """Compile every .cu to an object (in parallel) and link the shared library."""
+def build_library(force=False, verbose=False, check=False):
+    """Compile every .cu to an object (in parallel) and link the shared library.
+    ``check=True`` builds libmmsbm_b200_check.so with device-side bounds checks
+    (-DMMSBM_BOUNDS_CHECK); select it at run time with MMSBM_B200_LIB=<path>."""
     nvcc = _nvcc()
+    suffix, extra, lib = ("_chk.o", ["-DMMSBM_BOUNDS_CHECK"], LIB.replace(".so", "_check.so")) if check \
+        else (".o", ["-DNDEBUG"], LIB)
     headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "segment_pass.cuh"),
                os.path.join(HERE, "..", "include", "mmsbm_b200.h"), os.path.abspath(__file__)]
     objs, jobs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(CSRC, src[:-3] + ".o")
+        o = os.path.join(CSRC, src[:-3] + suffix)
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             jobs.append(cmd)
     if jobs:
         with cf.ThreadPoolExecutor(max_workers=len(jobs)) as ex:
@@ -52,14 +56,14 @@ def build_library(force=False, verbose=False):
                     sys.stderr.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
                 if res.returncode:
                     raise RuntimeError("nvcc failed for " + cmd[-3])
-    if jobs or force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    if jobs or force or _stale(lib, objs):
+        cmd = [nvcc, "-shared", "-o", lib] + objs + ["-lcudart"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode:
             sys.stderr.write(res.stdout + res.stderr)
             raise RuntimeError("link failed")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, check="--check" in sys.argv))

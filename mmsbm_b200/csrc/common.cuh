@@ -1,10 +1,20 @@
 // Shared helpers of libmmsbm_b200 (sm_100a only).
 #pragma once
+#include <assert.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 
 #include "../../include/mmsbm_b200.h"
+
+// Device-side bounds checks of every indirect access, compiled in by
+// `python -m mmsbm_b200.build --check` (libmmsbm_b200_check.so; compute-sanitizer is not
+// available on the GPU pool).  A failed check traps the kernel and surfaces as a CUDA error.
+#ifdef MMSBM_BOUNDS_CHECK
+#define MMSBM_DEV_CHECK(cond) assert(cond)
+#else
+#define MMSBM_DEV_CHECK(cond) ((void)0)
+#endif
 
 namespace mmsbm {
 

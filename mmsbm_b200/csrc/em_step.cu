@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(128) segment_fixup_kernel(const SegArgs A) {
   const int32_t* long_slot0 = long_seg + A.lmax;
   for (int li = blockIdx.x; li < n_long; li += gridDim.x) {
     const int sg = __ldg(long_seg + li), s0 = __ldg(long_slot0 + li), s1 = __ldg(long_slot0 + li + 1);
-    const double* src = A.partial + ((size_t)run * A.lmax + s0) * RNB;
+    MMSBM_DEV_CHECK(sg >= 0 && sg < A.nseg && s0 >= 0 && s0 < s1 && s1 <= A.smax);
+    const double* src = A.partial + ((size_t)run * A.smax + s0) * RNB;
     double* dst = A.wg + ((size_t)run * A.nseg + sg) * RNB;
     for (int o = threadIdx.x; o < RNB; o += blockDim.x) {
       double acc = 0.0;
@@ -526,7 +527,7 @@ struct EmDims {
   bool emit_items;   // the side with fewer segments carries the pr accumulation
   int nseg_e, NA_e, NBp_e;
   size_t p_elems, wg_u_elems, wg_i_elems, partial_elems, slots_u_elems, slots_i_elems;
-  int64_t lmax, pmax_u, pmax_i;
+  int64_t lmax, smax, pmax_u, pmax_i;
 };
 
 static EmDims em_dims(int64_t N, int U, int I, int R, int K, int L, int S) {
@@ -543,10 +544,11 @@ static EmDims em_dims(int64_t N, int U, int I, int R, int K, int L, int S) {
   d.wg_i_elems = (size_t)S * I * d.rnb_i;
   d.partial_elems = (size_t)S * kPrSlabs * d.NA_e * R * d.NBp_e;
   d.lmax = N / MMSBM_PIECE_LEN + 1;                 // must match graph_build.cu
+  d.smax = 2 * (N / MMSBM_PIECE_LEN) + 1;           // slots: at most deg/PIECE_LEN + 1 per long segment
   d.pmax_u = (int64_t)U + N / MMSBM_PIECE_LEN + 1;
   d.pmax_i = (int64_t)I + N / MMSBM_PIECE_LEN + 1;
-  d.slots_u_elems = (size_t)S * d.lmax * d.rnb_u;
-  d.slots_i_elems = (size_t)S * d.lmax * d.rnb_i;
+  d.slots_u_elems = (size_t)S * d.smax * d.rnb_u;
+  d.slots_i_elems = (size_t)S * d.smax * d.rnb_i;
   return d;
 }
 
@@ -621,7 +623,7 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
   MMSBM_MARK(1);
   // ---- by-user pass: g of every user (gathers eta rows) ----
   {
-    SegArgs a{useg, uadj, usched, eta, wg_u, slots_u, d.pmax_u, d.lmax, U, I, d.ldl, R, 0};
+    SegArgs a{useg, uadj, usched, eta, wg_u, slots_u, d.pmax_u, d.lmax, d.smax, U, I, d.ldl, R, 0};
     if ((rc = launch_segment_pass_and_fixup(a, N, S, st))) return rc;
   }
   MMSBM_MARK(2);
@@ -633,7 +635,7 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
   // ---- by-item pass: g of every item (gathers theta rows) ----
   if (ov) MMSBM_CUDA(cudaStreamWaitEvent(st, ov->e[1], 0));
   {
-    SegArgs a{iseg, iadj, isched, theta, wg_i, slots_i, d.pmax_i, d.lmax, I, U, d.ldk, R, 0};
+    SegArgs a{iseg, iadj, isched, theta, wg_i, slots_i, d.pmax_i, d.lmax, d.smax, I, U, d.ldk, R, 0};
     if ((rc = launch_segment_pass_and_fixup(a, N, S, st))) return rc;
   }
   MMSBM_MARK(3);

@@ -185,6 +185,7 @@ radix_scatter_kernel(const uint32_t* key, const uint32_t* val, int64_t n, int sh
     __syncwarp();
     if (on && rank == 0) off[warp][d] += __popc(peers);
     __syncwarp();
+    MMSBM_DEV_CHECK(!on || (dst >= 0 && dst < n));
     if (on) { key_out[dst] = k; val_out[dst] = v; }
   }
 }
@@ -194,6 +195,7 @@ __global__ void gather_adj_kernel(const uint32_t* perm, const int32_t* other, in
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   uint32_t p = perm[t];
+  MMSBM_DEV_CHECK(p < n);
   adj[t] = other[p];
   perm_out[t] = (int32_t)p;
 }
@@ -215,6 +217,8 @@ __global__ void set_last_kernel(int32_t* seg, int64_t nkeys, int32_t n) { seg[nk
 // sched layout (int32): [0] pieces P, [1] slots, [2] long segments, [3] piece length,
 //   piece_seg[Pmax] piece_idx[Pmax] piece_slot[Pmax] long_seg[Lmax] long_slot0[Lmax+1]
 __host__ __device__ inline int64_t sched_pmax(int64_t N, int64_t nseg) { return nseg + N / MMSBM_PIECE_LEN + 1; }
+// capacities: a long segment has > PIECE_LEN ratings, so there are at most N/PIECE_LEN of them;
+// each contributes ceil(deg/PIECE_LEN) <= deg/PIECE_LEN + 1 slots, i.e. at most 2N/PIECE_LEN slots
 __host__ __device__ inline int64_t sched_lmax(int64_t N) { return N / MMSBM_PIECE_LEN + 1; }
 
 __global__ void sched_count_kernel(const int32_t* deg, int nseg, int32_t* pps, int32_t* nslot, int32_t* nlong) {
@@ -240,6 +244,8 @@ __global__ void sched_fill_kernel(const int32_t* deg, int nseg, const int32_t* p
   int p = (deg[t] + MMSBM_PIECE_LEN - 1) / MMSBM_PIECE_LEN;
   if (p < 1) p = 1;
   const int pb = piece_base[t], sb = slot_base[t];
+  MMSBM_DEV_CHECK(pb >= 0 && pb + p <= pmax &&
+                  (p == 1 || (sb + p <= 2 * (lmax - 1) + 1 && long_base[t] < lmax)));
   for (int k = 0; k < p; ++k) {
     piece_seg[pb + k] = t;
     piece_idx[pb + k] = k;

@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(kLikWarps * 32) likelihood_kernel(const LikArg
       const double* Lr = Lq + (size_t)r * K * L;
       for (int j = lo; j < hi; ++j) {
         const int item = __ldg(A.uadj + j);
+        MMSBM_DEV_CHECK(item >= 0 && item < A.I);
         const double* erow = eta_run + (size_t)item * A.ldl;
         double tot = 0.0, s1 = 0.0, s2 = 0.0;   // sum w, sum w~ log w~, sum w~
         for (int l0 = 0; l0 < L; l0 += 32) {
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(256) prod_dist_kernel(const ProdArgs A) {
   const double* eta_run = A.eta + (size_t)run * A.I * A.ldl;
   for (int64_t m = (int64_t)blockIdx.x * nwarp + warp; m < A.M; m += (int64_t)gridDim.x * nwarp) {
     const int u = __ldg(A.user + m), it = __ldg(A.item + m);
+    MMSBM_DEV_CHECK(u >= 0 && u < A.U && it >= 0 && it < A.I);
     __syncwarp();
     for (int k = lane; k < K; k += 32) th[k] = __ldg(theta_run + (size_t)u * A.ldk + k);
     __syncwarp();

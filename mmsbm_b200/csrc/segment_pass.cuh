@@ -67,8 +67,8 @@ struct SegArgs {
   const int32_t* sched; // work schedule: pieces of <= MMSBM_PIECE_LEN ratings (graph_build.cu)
   const double* nbr;    // [S][nnbr][NBp]
   double* wg;           // [S][nseg][R*NBp]  in: w   out: g (in place; single-piece segments)
-  double* partial;      // [S][lmax][R*NBp]  out: g of the pieces of long segments, by slot
-  int64_t pmax, lmax;   // capacities of the schedule arrays
+  double* partial;      // [S][smax][R*NBp]  out: g of the pieces of long segments, by slot
+  int64_t pmax, lmax, smax;   // capacities: pieces, long segments, slots (graph_build.cu)
   int nseg, nnbr, NBp, R, segs_per_cta;
 };
 
@@ -151,7 +151,7 @@ segment_pass_kernel(const SegArgs A) {
   const int seg_hi = min(seg_lo + A.segs_per_cta, n_pieces);
   const double* nbr_run = A.nbr + (size_t)run * A.nnbr * NBp;
   double* wg_run = A.wg + (size_t)run * A.nseg * RNB;
-  double* part_run = A.partial + (size_t)run * A.lmax * RNB;
+  double* part_run = A.partial + (size_t)run * A.smax * RNB;
   int coff[CH];                                  // lane-constant chunk offsets (in doubles)
   bool con[CH];
 #pragma unroll
@@ -174,7 +174,9 @@ segment_pass_kernel(const SegArgs A) {
   int pi = seg_lo + warp, buf = 0;
   int sg = 0, pinfo_pref = 0, bend_pref = 0;
   auto prefetch_piece = [&](int p_, int b_, int& sg_out) {
+    MMSBM_DEV_CHECK(p_ >= 0 && p_ < A.pmax);
     sg_out = __ldg(piece_seg + p_);
+    MMSBM_DEV_CHECK(sg_out >= 0 && sg_out < A.nseg);
     pinfo_pref = (lane == 0) ? __ldg(piece_idx + p_) : (lane == 1) ? __ldg(piece_slot + p_) : 0;
     if (lane <= R) bend_pref = __ldg(A.seg + (size_t)sg_out * R + lane);
     fetch_w(sg_out, b_);
@@ -194,6 +196,7 @@ segment_pass_kernel(const SegArgs A) {
     const int slot = __shfl_sync(kFull, pinfo, 1);
     const int beg = __shfl_sync(kFull, bend_reg, 0) + __shfl_sync(kFull, pinfo, 0) * MMSBM_PIECE_LEN;
     const int end = min(beg + MMSBM_PIECE_LEN, __shfl_sync(kFull, bend_reg, R));
+    MMSBM_DEV_CHECK(slot >= -1 && slot < A.smax && beg >= 0 && beg <= end);
     // ids of the first chunk; slots past the end read row 0 (in bounds, weight zero)
     int cur_ids = 0;
     if (lane < SLOTS && beg + lane < end) cur_ids = ld_stream(A.adj + beg + lane);
@@ -245,6 +248,7 @@ segment_pass_kernel(const SegArgs A) {
 #pragma unroll
       for (int un = 0; un < UN; ++un) {
         const int id = __shfl_sync(kFull, cur_ids, (un * RPS + grp) & 31);
+        MMSBM_DEV_CHECK(id >= 0 && id < A.nnbr);
         const double* row = nbr_run + (size_t)id * NBp;
 #pragma unroll
         for (int c = 0; c < CH; ++c) x[un][c] = ldg256(row + coff[c]);
@@ -256,6 +260,7 @@ segment_pass_kernel(const SegArgs A) {
       }
       // ---- levels present in this chunk (rows are sorted by level; all warp-uniform) ----
       while (base >= nb) { ++lvl; nb = __shfl_sync(kFull, bend_reg, lvl + 1); }
+      MMSBM_DEV_CHECK(lvl >= 0 && lvl < R);
       const int last = min(base + SLOTS, end) - 1;
 
       if (last < nb && last - base == SLOTS - 1) {
@@ -293,6 +298,7 @@ segment_pass_kernel(const SegArgs A) {
         for (int un = 0; un < UN; ++un) {
           const int slot = un * RPS + grp;
           const int rs = __shfl_sync(kFull, r_slot, slot & 31);
+          MMSBM_DEV_CHECK(rs >= 0 && rs < R);
           double part = 0.0;
 #pragma unroll
           for (int c = 0; c < CH; ++c) {

@@ -196,6 +196,31 @@ def test_one_giant_segment_and_many_empty_levels():
         assert max(rel_err(th[s], rt), rel_err(et[s], re_), rel_err(prn[s], rp)) < PARAM_TOL
 
 
+@pytest.mark.parametrize("N,U,I,R,K,L", [(1, 1, 1, 1, 1, 1), (40, 1, 7, 1, 3, 2), (40, 6, 1, 3, 2, 4),
+                                         (500, 30, 20, 1, 5, 5), (64, 64, 64, 2, 2, 2)])
+def test_degenerate_shapes(N, U, I, R, K, L):
+    """One user, one item, one rating level, one row: every loop bound of the kernels at its edge."""
+    from mmsbm_b200.engine import Engine
+    data = random_triples(97, max(N, U, I, R), U, I, R)[:max(N, U, I, R)]
+    theta, eta, pr = random_params(101, U, I, K, L, R, S=2)
+    e = Engine(data, U, I, R, K, L)
+    e.set_params(theta, eta, pr)
+    e.run(2)
+    th, et, prn = e.get_params()
+    lik = e.likelihood()
+    fu, fi = orc.degree_factors(data, K, L)
+    for s in range(2):
+        t_, e_, p_ = theta[s], eta[s], pr[s]
+        for _ in range(2):
+            t_, e_, p_ = orc.em_iteration(data, t_, e_, p_, fu, fi)
+        assert max(rel_err(th[s], t_), rel_err(et[s], e_), rel_err(prn[s], p_)) < 1e-9
+        want = orc.likelihood(data, t_, e_, p_)
+        assert abs(lik[s] - want) <= LIK_TOL * abs(want) + 1e-15 * len(data) * K * L
+    rat = e.prod_dist_device(data).cpu().numpy()
+    for s in range(2):
+        assert rel_err(rat[s], orc.rating_distribution(data, th[s], et[s], prn[s])) < 1e-12
+
+
 def test_unsupported_shapes_fail_loudly():
     from mmsbm_b200._lib import MmsbmError
     from mmsbm_b200.engine import Engine
