@@ -329,8 +329,8 @@ def run_b200_arm(args, shape):
     value = updates_per_step * args.steps / (ms * 1e-3)
 
     # ---- per-kernel device time of one iteration (CUDA events inside the library) ----
-    ms4 = (ctypes.c_float * 6)()
-    acc = np.zeros(6)
+    ms4 = (ctypes.c_float * 7)()
+    acc = np.zeros(7)
     reps = 5
     for _ in range(reps):
         b = eng._alt
@@ -343,14 +343,15 @@ def run_b200_arm(args, shape):
     k_ms = acc / reps
     peak, peak_src = hbm_peak()
     alg_bytes = b_alg(U, I, N, K, L, S) * N * S           # both launches of segment_pass_kernel
-    seg_ms = float(k_ms[1] + k_ms[2])
+    seg_ms = float(k_ms[1] + k_ms[3])
     achieved = alg_bytes / (seg_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": None, "peak_source": peak_src, "kernel": "segment_pass_kernel (by-user + by-item launch)",
         "alg_bytes_per_update": b_alg(U, I, N, K, L, S),
-        "kernel_ms": {"p_tables_w_gemms": float(k_ms[0]), "by_user": float(k_ms[1]), "by_item": float(k_ms[2]),
-                      "n_gemms": float(k_ms[3]), "pr_accumulate": float(k_ms[4]), "pr_finalize": float(k_ms[5])},
+        "kernel_ms": {"p_tables_w": float(k_ms[0]), "by_user": float(k_ms[1]), "n_users": float(k_ms[2]),
+                      "by_item": float(k_ms[3]), "n_items": float(k_ms[4]), "pr_accumulate": float(k_ms[5]),
+                      "pr_finalize": float(k_ms[6])},
         "share_of_iteration": seg_ms / float(k_ms.sum()),
     }
     prof = os.path.join(ROOT, "profiles", "traffic.json")

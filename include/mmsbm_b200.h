@@ -108,8 +108,8 @@ int mmsbm_em_step(const int32_t* useg_dev, const int32_t* uadj_dev, const int32_
                   double* theta_out_dev, double* eta_out_dev, double* pr_out_dev,
                   int32_t flags, void* workspace_dev, size_t workspace_bytes, void* stream);
 /* the same step with CUDA events between its stages (measurement only: it waits for the
- * stream); ms6 = device ms of {P tables + w GEMMs, by-user pass, by-item pass, n GEMMs,
- * pr accumulate, pr finalize} */
+ * stream); ms7 = device ms of {P tables + w contractions, by-user pass, n contraction (users),
+ * by-item pass, n contraction (items), pr accumulate, pr finalize} */
 int mmsbm_em_step_profiled(const int32_t* useg_dev, const int32_t* uadj_dev, const int32_t* udeg_dev,
                            const int32_t* iseg_dev, const int32_t* iadj_dev, const int32_t* ideg_dev,
                            const int32_t* usched_dev, const int32_t* isched_dev,
@@ -118,7 +118,7 @@ int mmsbm_em_step_profiled(const int32_t* useg_dev, const int32_t* uadj_dev, con
                            const double* theta_dev, const double* eta_dev, const double* pr_dev,
                            double* theta_out_dev, double* eta_out_dev, double* pr_out_dev,
                            int32_t flags, void* workspace_dev, size_t workspace_bytes, void* stream,
-                           float* ms6);
+                           float* ms7);
 /* ``iterations`` steps ping-ponging between (theta,eta,pr)_a and _b, no host sync;
  * the result is in the _a buffers when iterations is even, else in _b.
  * Replaces the loop src/mmsbm.py:243-250. */

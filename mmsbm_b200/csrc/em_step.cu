@@ -37,7 +37,7 @@
 
 namespace mmsbm {
 
-constexpr int kPrSlabs = 64;
+constexpr int kPrSlabs = 128;
 constexpr int kPrThreads = 256;
 constexpr int kPrAcc = 8;       // accumulators per thread per output tile
 constexpr int kPrBatch = 16;    // segments staged per smem batch
@@ -337,30 +337,49 @@ struct PrFinArgs {
   int K, L, R, NA, NBp, transposed, normalize;
 };
 
-// one thread per (k,l): n_pr[k][l][r] = pr[k][l][r] * sum_slabs Acc; then the row over r is
-// divided by its sum (a sum that is exactly zero divides by one), expectation_maximization.py:154
-__global__ void pr_finalize_kernel(const PrFinArgs A) {
-  const int run = blockIdx.y;
-  const int kl = blockIdx.x * blockDim.x + threadIdx.x;
-  if (kl >= A.K * A.L) return;
-  const int k = kl / A.L, l = kl - k * A.L;
-  const int a = A.transposed ? l : k, b = A.transposed ? k : l;
+// One block per (owner index a, run): n_pr[a][b][r] = P * sum over slabs of Acc, then every
+// (k,l) row over r is divided by its sum (a sum that is exactly zero divides by one,
+// expectation_maximization.py:154).  Warp w adds its share of the slabs for 32 consecutive
+// outputs at a time (coalesced), the warps' sums are added in warp order: fixed order throughout.
+constexpr int kFinWarps = 8;
+__global__ void __launch_bounds__(kFinWarps * 32) pr_finalize_kernel(const PrFinArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int run = blockIdx.y, a = blockIdx.x;
   const int RNB = A.R * A.NBp, nout = A.NA * RNB;
-  const double* part = A.partial + (size_t)run * kPrSlabs * nout;
-  const double* prs = A.pr + ((size_t)run * A.K * A.L + kl) * A.R;
-  double* dst = A.pr_out + ((size_t)run * A.K * A.L + kl) * A.R;
-  double tot = 0.0;
-  for (int r = 0; r < A.R; ++r) {
+  double* part_s = reinterpret_cast<double*>(smem_raw);      // [kFinWarps][RNB]
+  double* tot_s = part_s + kFinWarps * RNB;                  // [RNB]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* part = A.partial + (size_t)run * kPrSlabs * nout + (size_t)a * RNB;
+  constexpr int per = kPrSlabs / kFinWarps;
+  for (int o = lane; o < RNB; o += 32) {
     double acc = 0.0;
-    const int o = a * RNB + r * A.NBp + b;
-    for (int s = 0; s < kPrSlabs; ++s) acc += part[(size_t)s * nout + o];
-    acc *= prs[r];
-    dst[r] = acc;
-    tot += acc;
+#pragma unroll 4
+    for (int s = warp * per; s < (warp + 1) * per; ++s) acc += part[(size_t)s * nout + o];
+    part_s[warp * RNB + o] = acc;
   }
-  if (A.normalize) {
-    const double d = (tot == 0.0) ? 1.0 : tot;
-    for (int r = 0; r < A.R; ++r) dst[r] = dst[r] / d;
+  __syncthreads();
+  for (int o = threadIdx.x; o < RNB; o += blockDim.x) {
+    double acc = 0.0;
+    for (int w = 0; w < kFinWarps; ++w) acc += part_s[w * RNB + o];
+    tot_s[o] = acc;
+  }
+  __syncthreads();
+  const int NB = A.transposed ? A.K : A.L;
+  for (int b = threadIdx.x; b < NB; b += blockDim.x) {
+    const int k = A.transposed ? b : a, l = A.transposed ? a : b;
+    const size_t kl = (size_t)k * A.L + l;
+    const double* prs = A.pr + ((size_t)run * A.K * A.L + kl) * A.R;
+    double* dst = A.pr_out + ((size_t)run * A.K * A.L + kl) * A.R;
+    double tot = 0.0;
+    for (int r = 0; r < A.R; ++r) {
+      const double v = tot_s[r * A.NBp + b] * prs[r];
+      dst[r] = v;
+      tot += v;
+    }
+    if (A.normalize) {
+      const double d = (tot == 0.0) ? 1.0 : tot;
+      for (int r = 0; r < A.R; ++r) dst[r] = dst[r] / d;
+    }
   }
 }
 
@@ -632,19 +651,20 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
   if ((rc = launch_n(wg_u, pn_u, theta, udeg, theta_out, U, d.ldk, d.rnb_u,
                      (flags & MMSBM_RAW_THETA) ? 0 : 1, S, s2))) return rc;
   MMSBM_SIDE_DONE(4);
+  MMSBM_MARK(3);
   // ---- by-item pass: g of every item (gathers theta rows) ----
   if (ov) MMSBM_CUDA(cudaStreamWaitEvent(st, ov->e[1], 0));
   {
     SegArgs a{iseg, iadj, isched, theta, wg_i, slots_i, d.pmax_i, d.lmax, d.smax, I, U, d.ldk, R, 0};
     if ((rc = launch_segment_pass_and_fixup(a, N, S, st))) return rc;
   }
-  MMSBM_MARK(3);
+  MMSBM_MARK(4);
   // eta' likewise; overlaps the pr kernels
   MMSBM_FORK(3);
   if ((rc = launch_n(wg_i, pn_i, eta, ideg, eta_out, I, d.ldl, d.rnb_i,
                      (flags & MMSBM_RAW_ETA_PR) ? 0 : 1, S, s2))) return rc;
   MMSBM_SIDE_DONE(5);
-  MMSBM_MARK(4);
+  MMSBM_MARK(5);
   // ---- pr' ----
   PrArgs pa{};
   pa.own = d.emit_items ? eta : theta;
@@ -657,16 +677,18 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
                                   (int)smem));
   pr_accumulate_kernel<<<dim3(kPrSlabs, S), kPrThreads, smem, st>>>(pa);
   MMSBM_LAUNCH_CHECK("pr_accumulate_kernel");
-  MMSBM_MARK(5);
+  MMSBM_MARK(6);
 
   PrFinArgs fa{};
   fa.partial = partial; fa.pr = pr; fa.pr_out = pr_out;
   fa.K = K; fa.L = L; fa.R = R; fa.NA = d.NA_e; fa.NBp = d.NBp_e;
   fa.transposed = d.emit_items ? 1 : 0;
   fa.normalize = (flags & MMSBM_RAW_ETA_PR) ? 0 : 1;
-  pr_finalize_kernel<<<dim3((K * L + 127) / 128, S), 128, 0, st>>>(fa);
+  const size_t fin_smem = (size_t)(kFinWarps + 1) * R * d.NBp_e * 8;
+  MMSBM_CUDA(cudaFuncSetAttribute(pr_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+  pr_finalize_kernel<<<dim3(d.NA_e, S), kFinWarps * 32, fin_smem, st>>>(fa);
   MMSBM_LAUNCH_CHECK("pr_finalize_kernel");
-  MMSBM_MARK(6);
+  MMSBM_MARK(7);
   if (ov) {                                                         // join: theta' and eta' are ready
     MMSBM_CUDA(cudaStreamWaitEvent(st, ov->e[4], 0));
     MMSBM_CUDA(cudaStreamWaitEvent(st, ov->e[5], 0));
@@ -690,8 +712,8 @@ extern "C" int mmsbm_em_step(const int32_t* useg, const int32_t* uadj, const int
 }
 
 // Same step with CUDA events between its stages; synchronises the stream and writes the device
-// time in ms of {P tables + w GEMMs, by-user pass, by-item pass, n GEMMs, pr accumulate,
-// pr finalize}.
+// time in ms of {P tables + w contractions, by-user pass, n contraction (users), by-item pass,
+// n contraction (items), pr accumulate, pr finalize}.
 extern "C" int mmsbm_em_step_profiled(const int32_t* useg, const int32_t* uadj, const int32_t* udeg,
                                       const int32_t* iseg, const int32_t* iadj, const int32_t* ideg, const int32_t* usched,
                  const int32_t* isched,
@@ -699,18 +721,18 @@ extern "C" int mmsbm_em_step_profiled(const int32_t* useg, const int32_t* uadj, 
                                       int32_t L, int32_t S, const double* theta, const double* eta,
                                       const double* pr, double* theta_out, double* eta_out,
                                       double* pr_out, int32_t flags, void* ws, size_t ws_bytes,
-                                      void* stream, float* ms6) {
-  MMSBM_REQUIRE(ms6, MMSBM_EINVAL, "mmsbm_em_step_profiled: null output");
-  cudaEvent_t ev[7];
-  for (int k = 0; k < 7; ++k) MMSBM_CUDA(cudaEventCreate(&ev[k]));
+                                      void* stream, float* ms7) {
+  MMSBM_REQUIRE(ms7, MMSBM_EINVAL, "mmsbm_em_step_profiled: null output");
+  cudaEvent_t ev[8];
+  for (int k = 0; k < 8; ++k) MMSBM_CUDA(cudaEventCreate(&ev[k]));
   int rc = em_step_impl(useg, uadj, udeg, iseg, iadj, ideg, usched, isched, N, U, I, R, K, L, S, theta, eta, pr,
                         theta_out, eta_out, pr_out, flags, ws, ws_bytes, stream, ev);
   if (rc == 0) {
-    cudaError_t e = cudaEventSynchronize(ev[6]);
+    cudaError_t e = cudaEventSynchronize(ev[7]);
     if (e != cudaSuccess) { set_error("cudaEventSynchronize: %s", cudaGetErrorString(e)); rc = (int)e; }
-    for (int k = 0; k < 6 && rc == 0; ++k) cudaEventElapsedTime(&ms6[k], ev[k], ev[k + 1]);
+    for (int k = 0; k < 7 && rc == 0; ++k) cudaEventElapsedTime(&ms7[k], ev[k], ev[k + 1]);
   }
-  for (int k = 0; k < 7; ++k) cudaEventDestroy(ev[k]);
+  for (int k = 0; k < 8; ++k) cudaEventDestroy(ev[k]);
   return rc;
 }
 
