@@ -38,8 +38,7 @@
 namespace mmsbm {
 
 constexpr int kPrSlabs = 128;
-constexpr int kPrThreads = 256;
-constexpr int kPrAcc = 8;       // accumulators per thread per output tile
+constexpr int kPrThreads = 128;
 constexpr int kPrBatch = 16;    // segments staged per smem batch
 constexpr int kGemmThreads = 256;
 constexpr int kGemmBK = 32;     // k-slab of the small GEMM (even)
@@ -284,48 +283,59 @@ struct PrArgs {
 };
 
 __global__ void __launch_bounds__(kPrThreads) pr_accumulate_kernel(const PrArgs A) {
+  // 4x4 register tiles (4 owner indices x 4 consecutive (r,b) outputs): per staged segment a
+  // thread reads two 32-byte vectors from shared memory for 16 FMAs
   extern __shared__ __align__(32) unsigned char smem_raw[];
-  double* own_s = reinterpret_cast<double*>(smem_raw);   // [kPrBatch][NA]
-  double* g_s = own_s + kPrBatch * A.NA;                 // [kPrBatch][RNB]
+  double* own_s = reinterpret_cast<double*>(smem_raw);   // [kPrBatch][lda]
+  double* g_s = own_s + kPrBatch * A.lda;                // [kPrBatch][RNB]
   const int run = blockIdx.y, slab = blockIdx.x;
   const int per = (A.nseg + kPrSlabs - 1) / kPrSlabs;
   const int s0 = slab * per, s1 = min(s0 + per, A.nseg);
   const int nout = A.NA * A.RNB;
+  const int ta = A.lda >> 2, tb = A.RNB >> 2, n_tiles = ta * tb;
   const double* own_run = A.own + (size_t)run * A.nseg * A.lda;
   const double* g_run = A.g + (size_t)run * A.nseg * A.RNB;
   double* dst = A.partial + ((size_t)run * kPrSlabs + slab) * nout;
 
-  for (int tile = 0; tile < nout; tile += kPrThreads * kPrAcc) {
-    double acc[kPrAcc];
-    int ia[kPrAcc], ib[kPrAcc];
+  for (int tile0 = 0; tile0 < n_tiles; tile0 += kPrThreads) {
+    const int tile = tile0 + threadIdx.x;
+    const bool on = tile < n_tiles;
+    const int a0 = on ? 4 * (tile / tb) : 0, b0 = on ? 4 * (tile % tb) : 0;
+    double acc[4][4];
 #pragma unroll
-    for (int t = 0; t < kPrAcc; ++t) {
-      acc[t] = 0.0;
-      int o = tile + t * kPrThreads + threadIdx.x;
-      int oc = min(o, nout - 1);
-      ia[t] = oc / A.RNB;
-      ib[t] = oc - ia[t] * A.RNB;
-    }
-    for (int b0 = s0; b0 < s1; b0 += kPrBatch) {
-      const int nb = min(kPrBatch, s1 - b0);
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[i][k] = 0.0;
+    for (int c0 = s0; c0 < s1; c0 += kPrBatch) {
+      const int nb = min(kPrBatch, s1 - c0);
       __syncthreads();
-      for (int t = threadIdx.x; t < nb * A.NA; t += kPrThreads) {
-        int sg = t / A.NA, a = t - sg * A.NA;
-        own_s[t] = __ldg(own_run + (size_t)(b0 + sg) * A.lda + a);
+      {   // rows of both tables are whole 16-byte pieces
+        const double2* src = reinterpret_cast<const double2*>(own_run + (size_t)c0 * A.lda);
+        double2* d2 = reinterpret_cast<double2*>(own_s);
+        for (int t = threadIdx.x; t < (nb * A.lda) >> 1; t += kPrThreads) d2[t] = __ldg(src + t);
+        src = reinterpret_cast<const double2*>(g_run + (size_t)c0 * A.RNB);
+        d2 = reinterpret_cast<double2*>(g_s);
+        for (int t = threadIdx.x; t < (nb * A.RNB) >> 1; t += kPrThreads) d2[t] = __ldg(src + t);
       }
-      for (int t = threadIdx.x; t < nb * A.RNB; t += kPrThreads)
-        g_s[t] = __ldg(g_run + (size_t)b0 * A.RNB + t);
       __syncthreads();
-      for (int sg = 0; sg < nb; ++sg) {
+      if (on) {
+        for (int sg = 0; sg < nb; ++sg) {
+          const double4_t o = lds32(own_s + sg * A.lda + a0);
+          const double4_t g = lds32(g_s + sg * A.RNB + b0);
+          const double ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-        for (int t = 0; t < kPrAcc; ++t)
-          acc[t] = fma(own_s[sg * A.NA + ia[t]], g_s[sg * A.RNB + ib[t]], acc[t]);
+          for (int i = 0; i < 4; ++i) {
+            acc[i][0] = fma(ov[i], g.x, acc[i][0]); acc[i][1] = fma(ov[i], g.y, acc[i][1]);
+            acc[i][2] = fma(ov[i], g.z, acc[i][2]); acc[i][3] = fma(ov[i], g.w, acc[i][3]);
+          }
+        }
       }
     }
+    if (on) {
 #pragma unroll
-    for (int t = 0; t < kPrAcc; ++t) {
-      int o = tile + t * kPrThreads + threadIdx.x;
-      if (o < nout) dst[o] = acc[t];
+      for (int i = 0; i < 4; ++i)
+        if (a0 + i < A.NA)
+          stg256(dst + (size_t)(a0 + i) * A.RNB + b0, double4_t{acc[i][0], acc[i][1], acc[i][2], acc[i][3]});
     }
   }
 }
@@ -672,7 +682,7 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
   pa.partial = partial;
   pa.nseg = d.nseg_e; pa.NA = d.NA_e; pa.lda = d.emit_items ? d.ldl : d.ldk;
   pa.RNB = R * d.NBp_e;
-  size_t smem = (size_t)kPrBatch * (pa.NA + pa.RNB) * 8;
+  size_t smem = (size_t)kPrBatch * (pa.lda + pa.RNB) * 8;
   MMSBM_CUDA(cudaFuncSetAttribute(pr_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
   pr_accumulate_kernel<<<dim3(kPrSlabs, S), kPrThreads, smem, st>>>(pa);
