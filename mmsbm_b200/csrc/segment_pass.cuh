@@ -15,8 +15,8 @@
 //
 // w comes from the W table (small_gemm_kernel) through cp.async, prefetched one segment ahead
 // into a double-buffered shared-memory row; g overwrites W in place.  Ratings are stored
-// grouped by level, so a chunk sees one level except where a boundary falls inside it; that
-// case reads w per row and repeats only the accumulation once per level present.
+// grouped by level and chunks never straddle a level boundary, so the level -- hence w -- is
+// warp-uniform inside a chunk.
 #pragma once
 #include "common.cuh"
 
@@ -242,12 +242,21 @@ segment_pass_kernel(const SegArgs A) {
       }
     };
 
-    for (int base = beg; base < end; base += SLOTS) {
+    // Chunks of up to SLOTS ratings that never straddle a level boundary: the level (hence w)
+    // is warp-uniform inside a chunk; the last chunk of a level is partial (its idle slots
+    // gather row 0 with weight zero).
+    for (int base = beg; base < end;) {
+      while (base >= nb) { ++lvl; nb = __shfl_sync(kFull, bend_reg, lvl + 1); }
+      MMSBM_DEV_CHECK(lvl >= 0 && lvl < R);
+      const int cend = min(min(base + SLOTS, nb), end);
+      const int cnt = cend - base;               // 1..SLOTS ratings in this chunk
       // ---- gather: one 256-bit load per (step, chunk) ----
       double4_t x[UN][CH];
 #pragma unroll
       for (int un = 0; un < UN; ++un) {
-        const int id = __shfl_sync(kFull, cur_ids, (un * RPS + grp) & 31);
+        const int slot = un * RPS + grp;
+        int id = __shfl_sync(kFull, cur_ids, slot & 31);
+        if (slot >= cnt) id = 0;                 // beyond the chunk: row 0 (in bounds), weight zero
         MMSBM_DEV_CHECK(id >= 0 && id < A.nnbr);
         const double* row = nbr_run + (size_t)id * NBp;
 #pragma unroll
@@ -255,77 +264,28 @@ segment_pass_kernel(const SegArgs A) {
       }
       // next chunk's ids (independent of the row loads above)
       {
-        const int nxt = base + SLOTS + lane;
+        const int nxt = cend + lane;
         cur_ids = (lane < SLOTS && nxt < end) ? ld_stream(A.adj + nxt) : 0;
       }
-      // ---- levels present in this chunk (rows are sorted by level; all warp-uniform) ----
-      while (base >= nb) { ++lvl; nb = __shfl_sync(kFull, bend_reg, lvl + 1); }
-      MMSBM_DEV_CHECK(lvl >= 0 && lvl < R);
-      const int last = min(base + SLOTS, end) - 1;
-
-      if (last < nb && last - base == SLOTS - 1) {
-        // ---- fast path: a full chunk of one level ----
-        while (cur_r < lvl) { flush(cur_r); ++cur_r; }
-        load_w(lvl);
+      while (cur_r < lvl) { flush(cur_r); ++cur_r; }
+      load_w(lvl);
 #pragma unroll
-        for (int un = 0; un < UN; ++un) {
-          double part = 0.0, part2 = 0.0;
+      for (int un = 0; un < UN; ++un) {
+        double part = 0.0, part2 = 0.0;
 #pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            part = fma(x[un][c].x, wr[c].x, part); part2 = fma(x[un][c].y, wr[c].y, part2);
-            part = fma(x[un][c].z, wr[c].z, part); part2 = fma(x[un][c].w, wr[c].w, part2);
-          }
-          const double im = rcp_clamped(group_sum(part + part2));
-#pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            g[c].x = fma(x[un][c].x, im, g[c].x); g[c].y = fma(x[un][c].y, im, g[c].y);
-            g[c].z = fma(x[un][c].z, im, g[c].z); g[c].w = fma(x[un][c].w, im, g[c].w);
-          }
+        for (int c = 0; c < CH; ++c) {
+          part = fma(x[un][c].x, wr[c].x, part); part2 = fma(x[un][c].y, wr[c].y, part2);
+          part = fma(x[un][c].z, wr[c].z, part); part2 = fma(x[un][c].w, wr[c].w, part2);
         }
-      } else {
-        // ---- general path: ragged tail and/or level boundaries inside the chunk ----
-        // every row takes the w of ITS level (per-lane shared-memory read), the E-step runs
-        // once; only the accumulation is repeated per level present, other levels weigh zero
-        int r_slot = 0;                          // level of slot `lane`
-        {
-          const int j = base + lane;
-          for (int r = 1; r < R; ++r) r_slot += (j >= __shfl_sync(kFull, bend_reg, r));
-        }
-        const int r_last = __shfl_sync(kFull, r_slot, last - base);
-        int r_mine[UN];
-        double rc[UN];
+        double im = rcp_clamped(group_sum(part + part2));
+        if (un * RPS + grp >= cnt) im = 0.0;     // idle slot (also the lanes past RPS*G)
 #pragma unroll
-        for (int un = 0; un < UN; ++un) {
-          const int slot = un * RPS + grp;
-          const int rs = __shfl_sync(kFull, r_slot, slot & 31);
-          MMSBM_DEV_CHECK(rs >= 0 && rs < R);
-          double part = 0.0;
-#pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            if (con[c]) {
-              const double4_t w = lds32(wb + rs * NBp + coff[c]);
-              part = fma(x[un][c].x, w.x, part); part = fma(x[un][c].y, w.y, part);
-              part = fma(x[un][c].z, w.z, part); part = fma(x[un][c].w, w.w, part);
-            }
-          }
-          rc[un] = rcp_clamped(group_sum(part));
-          r_mine[un] = (lane_on && base + slot <= last) ? rs : -1;   // -1 never matches a level
-        }
-        w_lvl = -1;                              // wr no longer describes a single level
-        for (int r = lvl;; ++r) {
-          while (cur_r < r) { flush(cur_r); ++cur_r; }
-#pragma unroll
-          for (int un = 0; un < UN; ++un) {
-            const double im = (r_mine[un] == r) ? rc[un] : 0.0;
-#pragma unroll
-            for (int c = 0; c < CH; ++c) {
-              g[c].x = fma(x[un][c].x, im, g[c].x); g[c].y = fma(x[un][c].y, im, g[c].y);
-              g[c].z = fma(x[un][c].z, im, g[c].z); g[c].w = fma(x[un][c].w, im, g[c].w);
-            }
-          }
-          if (r >= r_last) break;
+        for (int c = 0; c < CH; ++c) {
+          g[c].x = fma(x[un][c].x, im, g[c].x); g[c].y = fma(x[un][c].y, im, g[c].y);
+          g[c].z = fma(x[un][c].z, im, g[c].z); g[c].w = fma(x[un][c].w, im, g[c].w);
         }
       }
+      base = cend;
     }
     while (cur_r < R) { flush(cur_r); ++cur_r; }
     __syncwarp();
