@@ -420,6 +420,32 @@ def test_api_guards_and_helpers(tmp_path, monkeypatch):
     assert np.isfinite(mm.compute_likelihood(mm.train, res["theta"], res["eta"], res["pr"]))
 
 
+def test_reference_style_loop_through_the_plugin(golden_dir):
+    """The reference's own loop (src/mmsbm.py:243-256) driven through the plugin contract: every
+    iteration calls update_coefficients on host arrays, the driver normalises on the host, exactly
+    as MMSBM.run_one_sampling does with backend='b200' (level 1)."""
+    from mmsbm_b200 import ExpectationMaximization
+    g = _gold(golden_dir, "fixture.npz")
+    train = g["train"]
+    dims = {"n_samples": len(train), "n_user_groups": 2, "n_item_groups": 2, "n_ratings": 5}
+    em = ExpectationMaximization(dims, None, None, None,
+                                 {"user": g["norm_user"], "item": g["norm_item"]}, backend="b200")
+    assert em._backend == "b200"
+    theta, eta, pr = g["theta0"], g["eta0"], g["pr0"]
+    for _ in range(10):
+        n_theta, n_eta, npr = em.update_coefficients(data=train, theta=theta, eta=eta, pr=pr)
+        theta = em.normalize_with_d(n_theta, "user")
+        eta = em.normalize_with_d(n_eta, "item")
+        pr = em.normalize_with_self(npr)
+    assert rel_err(theta, g["theta10"]) < 1e-9 and rel_err(eta, g["eta10"]) < 1e-9
+    assert rel_err(pr, g["pr10"]) < 1e-9
+    lik = em.compute_likelihood(train, theta, eta, pr)
+    assert abs(lik - g["likelihood10"]) <= LIK_TOL * abs(g["likelihood10"])
+    rat = em.compute_prod_dist(g["test"], theta, eta, pr)
+    assert rel_err(rat, g["prediction"]) < 1e-9
+    assert rel_err(em.prod_dist(g["test"][0], theta, eta, pr), g["prediction"][0]) < 1e-9
+
+
 def test_reference_loader_contract():
     """load_backend returns the reference's 4-tuple; kernels_b200 at the repo root is the
     module the REFERENCE's loader would import for backend='b200'."""
