@@ -63,6 +63,22 @@ __global__ void __launch_bounds__(128) segment_fixup_kernel(const SegArgs A) {
   }
 }
 
+// ---- rows of run pairs interleaved: dst[pair][id][2][ld] <- src[2*pair + {0,1}][id][ld] --------
+__global__ void interleave_pairs_kernel(const double* __restrict__ src, double* __restrict__ dst, int n,
+                                        int ld, int pairs) {
+  const int c4 = ld >> 2;
+  const size_t total = (size_t)pairs * n * 2 * c4;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % c4);
+  const int rs = (int)((t / c4) & 1);
+  const size_t rest = t / c4 / 2;
+  const int id = (int)(rest % n);
+  const size_t p = rest / n;
+  const double4_t v = ldg256(src + (((size_t)(2 * p + rs) * n + id) * ld + 4 * c));
+  stg256(dst + 4 * t, v);
+}
+
 // ---- P in operand layout -------------------------------------------------------------------
 // For a side with owner dim NA (stride lda), neighbour dim NB (stride NBp), RNB = R*NBp and
 // o = r*NBp + b:   Pw[a][o] (lda x RNB)   Pn[o][a] (RNB x lda),  zero in every padded slot.
@@ -450,12 +466,43 @@ static int segs_per_cta_for(int nseg) {
   return e > 0 ? e : spc;
 }
 
-static int launch_segment_pass_impl(SegArgs a, int64_t n_ratings, int n_runs, cudaStream_t st) {
-  PassShape sh = choose_shape(a.NBp, (double)n_ratings / (double)a.nseg);
+// pairs of runs per warp whenever there are at least two runs and a lane holds one chunk
+static bool pairs_enabled(int NBp, int n_runs) {
+  return n_runs >= 2 && NBp <= 32 && env_int("MMSBM_PAIR", 1) != 0;
+}
+
+static int launch_segment_pass_impl(SegArgs a, const double* nbr_pairs, int64_t n_ratings, int n_runs,
+                                    cudaStream_t st) {
+  const double avg_degree = (double)n_ratings / (double)a.nseg;
+  PassShape sh = choose_shape(a.NBp, avg_degree);
   a.segs_per_cta = segs_per_cta_for(a.nseg);
   // the piece count lives on the device; size the grid for its upper bound (CTAs past it exit)
-  const dim3 grid((unsigned)((a.pmax + a.segs_per_cta - 1) / a.segs_per_cta), n_runs);
-  const size_t smem = seg_smem_bytes(a);
+  const unsigned gx = (unsigned)((a.pmax + a.segs_per_cta - 1) / a.segs_per_cta);
+  const int un_e = env_int("MMSBM_UN", 0), occ_e = env_int("MMSBM_OCC", 0);
+  int single_from = 0;                           // runs [single_from, n_runs) go one run per warp
+  if (nbr_pairs && pairs_enabled(a.NBp, n_runs)) {
+    const int pairs = n_runs / 2;
+    SegArgs p = a;
+    p.nbr = nbr_pairs;
+    p.run_base = 0;
+    const size_t smem = seg_smem_bytes(p, 2);
+    MMSBM_REQUIRE(smem <= 227 * 1024, MMSBM_ERANGE, "segment pass needs %zu bytes of shared memory", smem);
+    int UN = (sh.G == 1 || avg_degree < 256.0) ? 2 : 4, MINB = (avg_degree < 256.0) ? 4 : 3;
+    int rc = MMSBM_ERANGE;
+    if (un_e > 0 || occ_e > 0)
+      rc = launch_segment_pass_pair(p, sh.G, un_e > 0 ? un_e : UN, occ_e > 0 ? occ_e : MINB, dim3(gx, pairs), smem, st);
+    if (rc == MMSBM_ERANGE) rc = launch_segment_pass_pair(p, sh.G, UN, MINB, dim3(gx, pairs), smem, st);
+    if (rc == MMSBM_ERANGE && sh.G == 1) rc = launch_segment_pass_pair(p, sh.G, 2, 3, dim3(gx, pairs), smem, st);
+    if (rc) {
+      if (rc == MMSBM_ERANGE) set_error("no paired segment-pass variant for G=%d", sh.G);
+      return rc;
+    }
+    single_from = 2 * pairs;
+    if (single_from == n_runs) return 0;
+  }
+  a.run_base = single_from;
+  const dim3 grid(gx, n_runs - single_from);
+  const size_t smem = seg_smem_bytes(a, 1);
   MMSBM_REQUIRE(smem <= 227 * 1024, MMSBM_ERANGE,
                 "segment pass needs %zu bytes of shared memory (R=%d, row stride %d)", smem, a.R, a.NBp);
   auto go = [&](const PassShape& p) {
@@ -467,7 +514,6 @@ static int launch_segment_pass_impl(SegArgs a, int64_t n_ratings, int n_runs, cu
     }
   };
   // tuning overrides (only combinations that were instantiated take effect)
-  const int un_e = env_int("MMSBM_UN", 0), occ_e = env_int("MMSBM_OCC", 0);
   if (un_e > 0 || occ_e > 0) {
     PassShape alt = sh;
     if (un_e > 0) alt.UN = un_e;
@@ -480,8 +526,9 @@ static int launch_segment_pass_impl(SegArgs a, int64_t n_ratings, int n_runs, cu
   return rc;
 }
 
-static int launch_segment_pass_and_fixup(SegArgs a, int64_t n_ratings, int n_runs, cudaStream_t st) {
-  int rc = launch_segment_pass_impl(a, n_ratings, n_runs, st);
+static int launch_segment_pass_and_fixup(SegArgs a, const double* nbr_pairs, int64_t n_ratings, int n_runs,
+                                         cudaStream_t st) {
+  int rc = launch_segment_pass_impl(a, nbr_pairs, n_ratings, n_runs, st);
   if (rc) return rc;
   const unsigned gx = (unsigned)(a.lmax < 592 ? a.lmax : 592);
   segment_fixup_kernel<<<dim3(gx, n_runs), 128, 0, st>>>(a);
@@ -556,6 +603,7 @@ struct EmDims {
   bool emit_items;   // the side with fewer segments carries the pr accumulation
   int nseg_e, NA_e, NBp_e;
   size_t p_elems, wg_u_elems, wg_i_elems, partial_elems, slots_u_elems, slots_i_elems;
+  size_t th2_elems, et2_elems;   // theta / eta with the rows of run pairs interleaved
   int64_t lmax, smax, pmax_u, pmax_i;
 };
 
@@ -578,6 +626,8 @@ static EmDims em_dims(int64_t N, int U, int I, int R, int K, int L, int S) {
   d.pmax_i = (int64_t)I + N / MMSBM_PIECE_LEN + 1;
   d.slots_u_elems = (size_t)S * d.smax * d.rnb_u;
   d.slots_i_elems = (size_t)S * d.smax * d.rnb_i;
+  d.th2_elems = (size_t)(S / 2) * 2 * U * d.ldk;
+  d.et2_elems = (size_t)(S / 2) * 2 * I * d.ldl;
   return d;
 }
 
@@ -591,7 +641,8 @@ extern "C" int mmsbm_em_workspace_bytes(int64_t N, int32_t U, int32_t I, int32_t
                 "mmsbm_em_workspace_bytes: bad argument");
   EmDims d = em_dims(N, U, I, R, K, L, S);
   *bytes = 4 * align_up(d.p_elems * 8) + align_up(d.wg_u_elems * 8) + align_up(d.wg_i_elems * 8) +
-           align_up(d.partial_elems * 8) + align_up(d.slots_u_elems * 8) + align_up(d.slots_i_elems * 8) + 256;
+           align_up(d.partial_elems * 8) + align_up(d.slots_u_elems * 8) + align_up(d.slots_i_elems * 8) +
+           align_up(d.th2_elems * 8) + align_up(d.et2_elems * 8) + 256;
   return 0;
 }
 
@@ -628,7 +679,10 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
   double* partial = arena.take<double>(d.partial_elems);
   double* slots_u = arena.take<double>(d.slots_u_elems);
   double* slots_i = arena.take<double>(d.slots_i_elems);
-  MMSBM_REQUIRE(pw_u && pn_u && pw_i && pn_i && wg_u && wg_i && partial && slots_u && slots_i, MMSBM_ENOMEM,
+  double* th2 = arena.take<double>(d.th2_elems);
+  double* et2 = arena.take<double>(d.et2_elems);
+  MMSBM_REQUIRE(pw_u && pn_u && pw_i && pn_i && wg_u && wg_i && partial && slots_u && slots_i && th2 && et2,
+                MMSBM_ENOMEM,
                 "mmsbm_em_step: workspace too small (%zu)", ws_bytes);
   int rc;
 #define MMSBM_MARK(k) do { if (ev) MMSBM_CUDA(cudaEventRecord(ev[k], st)); } while (0)
@@ -645,6 +699,16 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
     prep_p_kernel<<<dim3((total + 255) / 256, S), 256, 0, st>>>(pr, K, L, R, d.ldk, d.ldl, pw_u, pn_u, pw_i, pn_i);
     MMSBM_LAUNCH_CHECK("prep_p_kernel");
     MMSBM_FORK(0);                                                  // side: after the P tables
+    if (pairs_enabled(d.ldl, S)) {     // eta rows of run pairs side by side (by-user pass gathers)
+      const size_t tot = (size_t)(S / 2) * I * 2 * (d.ldl / 4);
+      interleave_pairs_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(eta, et2, I, d.ldl, S / 2);
+      MMSBM_LAUNCH_CHECK("interleave_pairs_kernel");
+    }
+    if (pairs_enabled(d.ldk, S)) {     // theta rows likewise (by-item pass gathers)
+      const size_t tot = (size_t)(S / 2) * U * 2 * (d.ldk / 4);
+      interleave_pairs_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(theta, th2, U, d.ldk, S / 2);
+      MMSBM_LAUNCH_CHECK("interleave_pairs_kernel");
+    }
     if ((rc = launch_w(theta, pw_u, wg_u, U, d.ldk, d.rnb_u, S, st))) return rc;
     if ((rc = launch_w(eta, pw_i, wg_i, I, d.ldl, d.rnb_i, S, s2))) return rc;
     MMSBM_SIDE_DONE(1);                                             // w of the items ready
@@ -652,8 +716,8 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
   MMSBM_MARK(1);
   // ---- by-user pass: g of every user (gathers eta rows) ----
   {
-    SegArgs a{useg, uadj, usched, eta, wg_u, slots_u, d.pmax_u, d.lmax, d.smax, U, I, d.ldl, R, 0};
-    if ((rc = launch_segment_pass_and_fixup(a, N, S, st))) return rc;
+    SegArgs a{useg, uadj, usched, eta, wg_u, slots_u, d.pmax_u, d.lmax, d.smax, U, I, d.ldl, R, 0, 0};
+    if ((rc = launch_segment_pass_and_fixup(a, et2, N, S, st))) return rc;
   }
   MMSBM_MARK(2);
   // theta' = (g x Pn) o theta / max(deg,1): off the critical path, overlaps the by-item pass
@@ -665,8 +729,8 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
   // ---- by-item pass: g of every item (gathers theta rows) ----
   if (ov) MMSBM_CUDA(cudaStreamWaitEvent(st, ov->e[1], 0));
   {
-    SegArgs a{iseg, iadj, isched, theta, wg_i, slots_i, d.pmax_i, d.lmax, d.smax, I, U, d.ldk, R, 0};
-    if ((rc = launch_segment_pass_and_fixup(a, N, S, st))) return rc;
+    SegArgs a{iseg, iadj, isched, theta, wg_i, slots_i, d.pmax_i, d.lmax, d.smax, I, U, d.ldk, R, 0, 0};
+    if ((rc = launch_segment_pass_and_fixup(a, th2, N, S, st))) return rc;
   }
   MMSBM_MARK(4);
   // eta' likewise; overlaps the pr kernels

@@ -65,15 +65,16 @@ struct SegArgs {
   const int32_t* seg;   // [nseg*R+1]
   const int32_t* adj;   // [N] neighbour ids, grouped by (segment, level)
   const int32_t* sched; // work schedule: pieces of <= MMSBM_PIECE_LEN ratings (graph_build.cu)
-  const double* nbr;    // [S][nnbr][NBp]
+  const double* nbr;    // RUNS == 1: [S][nnbr][NBp]   RUNS == 2: [S/2][nnbr][2][NBp] (runs interleaved)
   double* wg;           // [S][nseg][R*NBp]  in: w   out: g (in place; single-piece segments)
   double* partial;      // [S][smax][R*NBp]  out: g of the pieces of long segments, by slot
   int64_t pmax, lmax, smax;   // capacities: pieces, long segments, slots (graph_build.cu)
   int nseg, nnbr, NBp, R, segs_per_cta;
+  int run_base;         // first run of this launch (grid.y counts runs, or pairs of runs)
 };
 
-inline size_t seg_smem_bytes(const SegArgs& a) {
-  return (size_t)kWarps * 2 * a.R * a.NBp * 8 + 32;
+inline size_t seg_smem_bytes(const SegArgs& a, int runs) {
+  return (size_t)kWarps * 2 * runs * a.R * a.NBp * 8 + 32;
 }
 
 // Sum of `part` over the G consecutive lanes of a group, delivered to every lane of the group.
@@ -122,26 +123,32 @@ struct GroupSum {
   }
 };
 
-template <int G, int CH, int UN, int MINB>
+// RUNS == 2: a warp serves the same piece for a PAIR of runs.  The neighbour rows of the two
+// runs are interleaved in memory, so a rating's gather is one contiguous 2*8*NB-byte read
+// (fewer L1 wavefronts per byte than two separate rows), and the index loads, the level
+// bookkeeping and the cross-group reductions are shared by the two runs.
+template <int G, int CH, int UN, int MINB, int RUNS>
 __global__ void __launch_bounds__(kWarps * 32, MINB)
 segment_pass_kernel(const SegArgs A) {
-  constexpr int RPS = 32 / G;                    // ratings per step
+  constexpr int GR = G * RUNS;                   // lanes per rating
+  constexpr int RPS = 32 / GR;                   // ratings per step
   constexpr int SLOTS = UN * RPS;                // ratings per chunk of work (<= 32)
   static_assert(SLOTS <= 32, "a chunk's ids must fit one coalesced 32-lane load");
   extern __shared__ __align__(32) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int run = blockIdx.y;
   // one chunk per lane means the row stride is exactly 4*G doubles: a compile-time constant
   const int R = A.R, NBp = (CH == 1) ? 4 * G : A.NBp, RNB = R * NBp;
   const int NCH = NBp >> 2;                      // 32-byte chunks per neighbour row
 
-  double* wbuf = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 2 * RNB;   // [2][RNB]
-  int* ctr = reinterpret_cast<int*>(smem_raw + (size_t)kWarps * 2 * RNB * 8);
+  double* wbuf = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 2 * RUNS * RNB;   // [2][RUNS][RNB]
+  int* ctr = reinterpret_cast<int*>(smem_raw + (size_t)kWarps * 2 * RUNS * RNB * 8);
   if (threadIdx.x == 0) *ctr = kWarps;           // warps start on segments 0..kWarps-1
   __syncthreads();
 
-  const int grp = lane / G, q = lane - grp * G;
-  const bool lane_on = grp < RPS;                // lanes past RPS*G idle (32 % G of them)
+  const int grp = lane / GR, lig = lane - grp * GR;
+  const int rsel = lig / G, q = lig - rsel * G;  // which run of the pair, which lane of the group
+  const bool lane_on = grp < RPS;                // lanes past RPS*GR idle (32 % GR of them)
+  const int run0 = A.run_base + blockIdx.y * RUNS, run = run0 + rsel;
   // this CTA's range of pieces (a piece = up to MMSBM_PIECE_LEN ratings of one segment)
   const int32_t* piece_seg = A.sched + 4;
   const int32_t* piece_idx = piece_seg + A.pmax;
@@ -149,7 +156,9 @@ segment_pass_kernel(const SegArgs A) {
   const int n_pieces = __ldg(A.sched);
   const int seg_lo = blockIdx.x * A.segs_per_cta;
   const int seg_hi = min(seg_lo + A.segs_per_cta, n_pieces);
-  const double* nbr_run = A.nbr + (size_t)run * A.nnbr * NBp;
+  // base of this lane's neighbour rows: row(id) = nbr_run + id * RUNS * NBp
+  const double* nbr_run = (RUNS == 1) ? A.nbr + (size_t)run * A.nnbr * NBp
+                                      : A.nbr + ((size_t)blockIdx.y * A.nnbr * RUNS + rsel) * NBp;
   double* wg_run = A.wg + (size_t)run * A.nseg * RNB;
   double* part_run = A.partial + (size_t)run * A.smax * RNB;
   int coff[CH];                                  // lane-constant chunk offsets (in doubles)
@@ -160,13 +169,16 @@ segment_pass_kernel(const SegArgs A) {
     con[c] = lane_on && chunk < NCH;
     coff[c] = con[c] ? 4 * chunk : 0;            // idle lanes re-read chunk 0 (same line)
   }
-  const GroupSum<G> group_sum(grp * G, q);
+  const GroupSum<G> group_sum(grp * GR + rsel * G, q);
 
-  // w row of a segment -> shared memory, asynchronously (16-byte pieces)
+  // w rows (one per run) of a segment -> shared memory, asynchronously (16-byte pieces)
   auto fetch_w = [&](int s_, int b_) {
-    const double* src = wg_run + (size_t)s_ * RNB;
-    double* dst = wbuf + (size_t)b_ * RNB;
-    for (int p = lane; p < (RNB >> 1); p += 32) cp_async16(dst + 2 * p, src + 2 * p);
+#pragma unroll
+    for (int r2 = 0; r2 < RUNS; ++r2) {
+      const double* src = A.wg + ((size_t)(run0 + r2) * A.nseg + s_) * RNB;
+      double* dst = wbuf + (size_t)(b_ * RUNS + r2) * RNB;
+      for (int p = lane; p < (RNB >> 1); p += 32) cp_async16(dst + 2 * p, src + 2 * p);
+    }
   };
 
   // prefetched state of a piece: its segment, (piece number, slot) in lanes 0 and 1, and the
@@ -202,7 +214,7 @@ segment_pass_kernel(const SegArgs A) {
     if (lane < SLOTS && beg + lane < end) cur_ids = ld_stream(A.adj + beg + lane);
     cp_async_wait<1>();                          // this segment's w has landed
     __syncwarp();
-    const double* wb = wbuf + (size_t)buf * RNB;
+    const double* wb = wbuf + (size_t)(buf * RUNS + rsel) * RNB;
     double* gout = (slot < 0) ? wg_run + (size_t)sg * RNB : part_run + (size_t)slot * RNB;
 
     int cur_r = 0;                               // level the accumulators g belong to
@@ -222,10 +234,10 @@ segment_pass_kernel(const SegArgs A) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
           if (off < RPS) {
-            const double tx = __shfl_down_sync(kFull, v.x, off * G);
-            const double ty = __shfl_down_sync(kFull, v.y, off * G);
-            const double tz = __shfl_down_sync(kFull, v.z, off * G);
-            const double tw = __shfl_down_sync(kFull, v.w, off * G);
+            const double tx = __shfl_down_sync(kFull, v.x, off * GR);
+            const double ty = __shfl_down_sync(kFull, v.y, off * GR);
+            const double tz = __shfl_down_sync(kFull, v.z, off * GR);
+            const double tw = __shfl_down_sync(kFull, v.w, off * GR);
             if (grp + off < RPS) { v.x += tx; v.y += ty; v.z += tz; v.w += tw; }
           }
         }
@@ -258,7 +270,7 @@ segment_pass_kernel(const SegArgs A) {
         int id = __shfl_sync(kFull, cur_ids, slot & 31);
         if (slot >= cnt) id = 0;                 // beyond the chunk: row 0 (in bounds), weight zero
         MMSBM_DEV_CHECK(id >= 0 && id < A.nnbr);
-        const double* row = nbr_run + (size_t)id * NBp;
+        const double* row = nbr_run + (size_t)id * (RUNS * NBp);
 #pragma unroll
         for (int c = 0; c < CH; ++c) x[un][c] = ldg256(row + coff[c]);
       }
@@ -278,7 +290,7 @@ segment_pass_kernel(const SegArgs A) {
           part = fma(x[un][c].z, wr[c].z, part); part2 = fma(x[un][c].w, wr[c].w, part2);
         }
         double im = rcp_clamped(group_sum(part + part2));
-        if (un * RPS + grp >= cnt) im = 0.0;     // idle slot (also the lanes past RPS*G)
+        if (un * RPS + grp >= cnt) im = 0.0;     // idle slot (also the lanes past RPS*GR)
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           g[c].x = fma(x[un][c].x, im, g[c].x); g[c].y = fma(x[un][c].y, im, g[c].y);
@@ -298,13 +310,15 @@ segment_pass_kernel(const SegArgs A) {
 
 // one instantiation unit per CH (seg_inst_ch*.cu) keeps compile time parallel
 int launch_segment_pass_ch1(const SegArgs& a, int G, int UN, int MINB, dim3 grid, size_t smem, cudaStream_t st);
+int launch_segment_pass_pair(const SegArgs& a, int G, int UN, int MINB, dim3 grid, size_t smem, cudaStream_t st);
 int launch_segment_pass_ch2(const SegArgs& a, int G, int UN, int MINB, dim3 grid, size_t smem, cudaStream_t st);
 int launch_segment_pass_ch4(const SegArgs& a, int G, int UN, int MINB, dim3 grid, size_t smem, cudaStream_t st);
 int launch_segment_pass_ch8(const SegArgs& a, int G, int UN, int MINB, dim3 grid, size_t smem, cudaStream_t st);
 
-#define MMSBM_SEG_LAUNCH(Gv, CHv, UNv, MBv)                                                    \
+#define MMSBM_SEG_LAUNCH(Gv, CHv, UNv, MBv) MMSBM_SEG_LAUNCH_R(Gv, CHv, UNv, MBv, 1)
+#define MMSBM_SEG_LAUNCH_R(Gv, CHv, UNv, MBv, RUNSv)                                           \
   if (G == Gv && UN == UNv && MINB == MBv) {                                                   \
-    auto kern = segment_pass_kernel<Gv, CHv, UNv, MBv>;                                        \
+    auto kern = segment_pass_kernel<Gv, CHv, UNv, MBv, RUNSv>;                                 \
     MMSBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, dim3(kWarps * 32), smem, st>>>(a);                                            \
     MMSBM_LAUNCH_CHECK("segment_pass_kernel");                                                 \
