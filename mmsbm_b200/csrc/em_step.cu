@@ -449,9 +449,10 @@ static PassShape choose_shape(int NBp, double avg_degree) {
   }
   const int G = (NCH + CH - 1) / CH;
   PassShape sh{G, CH, 1, 1};   // CH == 1 implies NBp == 4*G (the kernel relies on it)
-  if (CH == 1) { sh.UN = (G == 1) ? 1 : 2; sh.MINB = 3; }
-  // short segments are latency bound: one step in flight but 4 CTAs/SM wins there (G = 5 only)
-  if (CH == 1 && G == 5 && avg_degree < 256.0) { sh.UN = 1; sh.MINB = 4; }
+  // three row loads in flight per warp (a fourth is not issued back to back by ptxas: the
+  // warp's scoreboards are taken), 3 CTAs/SM: best of the UN x MINB sweep on both passes
+  (void)avg_degree;
+  if (CH == 1) { sh.UN = (G == 1) ? 1 : (G == 2) ? 2 : 3; sh.MINB = 3; }   // UN * (32 / G) <= 32
   else if (CH == 2) { sh.UN = 1; sh.MINB = 3; }
   return sh;
 }
@@ -487,7 +488,7 @@ static int launch_segment_pass_impl(SegArgs a, const double* nbr_pairs, int64_t 
     p.run_base = 0;
     const size_t smem = seg_smem_bytes(p, 2);
     MMSBM_REQUIRE(smem <= 227 * 1024, MMSBM_ERANGE, "segment pass needs %zu bytes of shared memory", smem);
-    int UN = (sh.G == 1 || avg_degree < 256.0) ? 2 : 4, MINB = (avg_degree < 256.0) ? 4 : 3;
+    int UN = (sh.G == 1) ? 2 : 3, MINB = 3;                     // UN * (32 / 2G) <= 32
     int rc = MMSBM_ERANGE;
     if (un_e > 0 || occ_e > 0)
       rc = launch_segment_pass_pair(p, sh.G, un_e > 0 ? un_e : UN, occ_e > 0 ? occ_e : MINB, dim3(gx, pairs), smem, st);

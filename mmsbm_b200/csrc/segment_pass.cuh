@@ -18,6 +18,8 @@
 // grouped by level and chunks never straddle a level boundary, so the level -- hence w -- is
 // warp-uniform inside a chunk.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mmsbm {
@@ -29,8 +31,8 @@ struct alignas(16) double4_t { double x, y, z, w; };
 // 256-bit read-only load (LDG.E.ENL2.256 on sm_100a): a lane's 32-byte chunk of a row
 __device__ __forceinline__ double4_t ldg256(const double* p) {
   double4_t v;
-  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
-               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+      : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
   return v;
 }
 __device__ __forceinline__ void stg256(double* p, const double4_t& v) {
@@ -159,8 +161,6 @@ segment_pass_kernel(const SegArgs A) {
   // base of this lane's neighbour rows: row(id) = nbr_run + id * RUNS * NBp
   const double* nbr_run = (RUNS == 1) ? A.nbr + (size_t)run * A.nnbr * NBp
                                       : A.nbr + ((size_t)blockIdx.y * A.nnbr * RUNS + rsel) * NBp;
-  double* wg_run = A.wg + (size_t)run * A.nseg * RNB;
-  double* part_run = A.partial + (size_t)run * A.smax * RNB;
   int coff[CH];                                  // lane-constant chunk offsets (in doubles)
   bool con[CH];
 #pragma unroll
@@ -173,10 +173,11 @@ segment_pass_kernel(const SegArgs A) {
 
   // w rows (one per run) of a segment -> shared memory, asynchronously (16-byte pieces)
   auto fetch_w = [&](int s_, int b_) {
-#pragma unroll
+#pragma unroll 1
     for (int r2 = 0; r2 < RUNS; ++r2) {
       const double* src = A.wg + ((size_t)(run0 + r2) * A.nseg + s_) * RNB;
       double* dst = wbuf + (size_t)(b_ * RUNS + r2) * RNB;
+#pragma unroll 1
       for (int p = lane; p < (RNB >> 1); p += 32) cp_async16(dst + 2 * p, src + 2 * p);
     }
   };
@@ -215,91 +216,107 @@ segment_pass_kernel(const SegArgs A) {
     cp_async_wait<1>();                          // this segment's w has landed
     __syncwarp();
     const double* wb = wbuf + (size_t)(buf * RUNS + rsel) * RNB;
-    double* gout = (slot < 0) ? wg_run + (size_t)sg * RNB : part_run + (size_t)slot * RNB;
+    double* gout = (slot < 0) ? A.wg + ((size_t)run * A.nseg + sg) * RNB
+                              : A.partial + ((size_t)run * A.smax + slot) * RNB;
 
-    int cur_r = 0;                               // level the accumulators g belong to
-    int lvl = 0, nb = __shfl_sync(kFull, bend_reg, 1);   // level of the chunk's first row, its end
-    int w_lvl = -1;                              // level whose w chunks sit in wr (warp-uniform)
     double4_t g[CH], wr[CH];
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      g[c] = double4_t{0.0, 0.0, 0.0, 0.0};
-      wr[c] = double4_t{0.0, 0.0, 0.0, 0.0};
-    }
-
-    auto flush = [&](int r) {                    // g_r: sum over the groups, then to global
+    auto flush = [&](int r, bool any) {          // g_r: sum over the groups, then to global
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
         double4_t v = g[c];
+        if (any) {                               // warp-uniform; an empty level stores zeros
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          if (off < RPS) {
-            const double tx = __shfl_down_sync(kFull, v.x, off * GR);
-            const double ty = __shfl_down_sync(kFull, v.y, off * GR);
-            const double tz = __shfl_down_sync(kFull, v.z, off * GR);
-            const double tw = __shfl_down_sync(kFull, v.w, off * GR);
-            if (grp + off < RPS) { v.x += tx; v.y += ty; v.z += tz; v.w += tw; }
+          for (int off = 16; off > 0; off >>= 1) {
+            if (off < RPS) {
+              const double tx = __shfl_down_sync(kFull, v.x, off * GR);
+              const double ty = __shfl_down_sync(kFull, v.y, off * GR);
+              const double tz = __shfl_down_sync(kFull, v.z, off * GR);
+              const double tw = __shfl_down_sync(kFull, v.w, off * GR);
+              if (grp + off < RPS) { v.x += tx; v.y += ty; v.z += tz; v.w += tw; }
+            }
           }
         }
         if (grp == 0 && con[c]) stg256(gout + r * NBp + coff[c], v);
-        g[c] = double4_t{0.0, 0.0, 0.0, 0.0};
-      }
-    };
-    auto load_w = [&](int r) {                   // this lane's chunks of w_r (warp-uniform r)
-      if (w_lvl != r) {
-        w_lvl = r;
-#pragma unroll
-        for (int c = 0; c < CH; ++c)
-          if (con[c]) wr[c] = lds32(wb + r * NBp + coff[c]);
       }
     };
 
-    // Chunks of up to SLOTS ratings that never straddle a level boundary: the level (hence w)
-    // is warp-uniform inside a chunk; the last chunk of a level is partial (its idle slots
-    // gather row 0 with weight zero).
-    for (int base = beg; base < end;) {
-      while (base >= nb) { ++lvl; nb = __shfl_sync(kFull, bend_reg, lvl + 1); }
-      MMSBM_DEV_CHECK(lvl >= 0 && lvl < R);
-      const int cend = min(min(base + SLOTS, nb), end);
-      const int cnt = cend - base;               // 1..SLOTS ratings in this chunk
-      // ---- gather: one 256-bit load per (step, chunk) ----
-      double4_t x[UN][CH];
+    // Level-major: the ratings of a segment are stored grouped by level, so the piece is the
+    // concatenation of (at most R) level runs.  Each run is cut into chunks of up to SLOTS
+    // ratings -- the level, hence w, is warp-uniform inside a chunk; the last chunk of a run is
+    // partial (its idle slots gather row 0 with weight zero).
+    int lo = beg;                                // start of the part of the piece not yet done
+    for (int r = 0; r < R; ++r) {
+      const int le = min(end, __shfl_sync(kFull, bend_reg, r + 1));   // end of level r in the piece
 #pragma unroll
-      for (int un = 0; un < UN; ++un) {
-        const int slot = un * RPS + grp;
-        int id = __shfl_sync(kFull, cur_ids, slot & 31);
-        if (slot >= cnt) id = 0;                 // beyond the chunk: row 0 (in bounds), weight zero
-        MMSBM_DEV_CHECK(id >= 0 && id < A.nnbr);
-        const double* row = nbr_run + (size_t)id * (RUNS * NBp);
+      for (int c = 0; c < CH; ++c) g[c] = double4_t{0.0, 0.0, 0.0, 0.0};
+      const bool any = lo < le;
+      if (any) {
 #pragma unroll
-        for (int c = 0; c < CH; ++c) x[un][c] = ldg256(row + coff[c]);
-      }
-      // next chunk's ids (independent of the row loads above)
-      {
-        const int nxt = cend + lane;
-        cur_ids = (lane < SLOTS && nxt < end) ? ld_stream(A.adj + nxt) : 0;
-      }
-      while (cur_r < lvl) { flush(cur_r); ++cur_r; }
-      load_w(lvl);
+        for (int c = 0; c < CH; ++c)
+          wr[c] = con[c] ? lds32(wb + r * NBp + coff[c]) : double4_t{0.0, 0.0, 0.0, 0.0};
+        for (int base = lo; base < le; base += SLOTS) {
+          const int cnt = min(SLOTS, le - base); // 1..SLOTS ratings in this chunk
+          // NS = steps of this chunk that hold ratings (the tail chunk of a level has fewer)
+          auto chunk = [&](auto ns_tag) {
+            constexpr int NS = decltype(ns_tag)::value;
+            // ---- gather: one 256-bit load per (step, chunk) ----
+            double4_t x[NS][CH];
 #pragma unroll
-      for (int un = 0; un < UN; ++un) {
-        double part = 0.0, part2 = 0.0;
+            for (int un = 0; un < NS; ++un) {
+              const int sl = un * RPS + grp;
+              int id = __shfl_sync(kFull, cur_ids, sl & 31);
+              if (sl >= cnt) id = 0;             // beyond the chunk: row 0 (in bounds), weight zero
+              MMSBM_DEV_CHECK(id >= 0 && id < A.nnbr);
+              const double* row = nbr_run + (size_t)id * (RUNS * NBp);
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          part = fma(x[un][c].x, wr[c].x, part); part2 = fma(x[un][c].y, wr[c].y, part2);
-          part = fma(x[un][c].z, wr[c].z, part); part2 = fma(x[un][c].w, wr[c].w, part2);
+              for (int c = 0; c < CH; ++c) x[un][c] = ldg256(row + coff[c]);
+            }
+            // next chunk's ids (independent of the row loads above); the next chunk starts
+            // where this one ends, whatever its level
+            {
+              const int nxt = base + cnt + lane;
+              cur_ids = (lane < SLOTS && nxt < end) ? ld_stream(A.adj + nxt) : 0;
+            }
+            // all dots first, then the reciprocals, then the accumulation: every row is needed
+            // by the first phase, so the loads are issued back to back
+            double im[NS];
+#pragma unroll
+            for (int un = 0; un < NS; ++un) {
+              double part = 0.0, part2 = 0.0;
+#pragma unroll
+              for (int c = 0; c < CH; ++c) {
+                part = fma(x[un][c].x, wr[c].x, part); part2 = fma(x[un][c].y, wr[c].y, part2);
+                part = fma(x[un][c].z, wr[c].z, part); part2 = fma(x[un][c].w, wr[c].w, part2);
+              }
+              im[un] = part + part2;
+            }
+#pragma unroll
+            for (int un = 0; un < NS; ++un) {
+              im[un] = rcp_clamped(group_sum(im[un]));
+              if (un * RPS + grp >= cnt) im[un] = 0.0;   // idle slot (also the lanes past RPS*GR)
+            }
+#pragma unroll
+            for (int un = 0; un < NS; ++un) {
+#pragma unroll
+              for (int c = 0; c < CH; ++c) {
+                g[c].x = fma(x[un][c].x, im[un], g[c].x); g[c].y = fma(x[un][c].y, im[un], g[c].y);
+                g[c].z = fma(x[un][c].z, im[un], g[c].z); g[c].w = fma(x[un][c].w, im[un], g[c].w);
+              }
+            }
+          };
+          if (cnt > (UN - 1) * RPS) chunk(std::integral_constant<int, UN>{});
+          else if constexpr (UN >= 2) {
+            if (UN == 2 || cnt <= RPS) chunk(std::integral_constant<int, 1>{});
+            else if constexpr (UN >= 3) {
+              if (UN == 3 || cnt <= 2 * RPS) chunk(std::integral_constant<int, 2>{});
+              else if constexpr (UN >= 4) chunk(std::integral_constant<int, 3>{});
+            }
+          }
         }
-        double im = rcp_clamped(group_sum(part + part2));
-        if (un * RPS + grp >= cnt) im = 0.0;     // idle slot (also the lanes past RPS*GR)
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          g[c].x = fma(x[un][c].x, im, g[c].x); g[c].y = fma(x[un][c].y, im, g[c].y);
-          g[c].z = fma(x[un][c].z, im, g[c].z); g[c].w = fma(x[un][c].w, im, g[c].w);
-        }
+        lo = le;
       }
-      base = cend;
+      flush(r, any);
     }
-    while (cur_r < R) { flush(cur_r); ++cur_r; }
     __syncwarp();
     buf ^= 1;
     sg = sg_next;
