@@ -204,7 +204,9 @@ __global__ void __launch_bounds__(kGemmThreads) small_gemm_kernel(const GemmArgs
 // so the kernels need no barriers and little LSU bandwidth; HBM traffic is the W / G rows.
 constexpr int kRowThreads = 256;
 
-template <int LD>
+// ROWS rows per lane: every 32-byte read of P from shared memory (a warp broadcast) feeds
+// 4*ROWS DFMAs, so with two rows the fp64 pipe, not the shared-memory pipe, sets the pace.
+template <int LD, int ROWS>
 __global__ void __launch_bounds__(kRowThreads) row_w_kernel(const double* __restrict__ own,
                                                             const double* __restrict__ pw,
                                                             double* __restrict__ W, int M, int RNB) {
@@ -219,28 +221,40 @@ __global__ void __launch_bounds__(kRowThreads) row_w_kernel(const double* __rest
   __syncthreads();
   const double* own_run = own + (size_t)run * M * LD;
   double* w_run = W + (size_t)run * M * RNB;
-  for (int m = blockIdx.x * kRowThreads + threadIdx.x; m < M; m += gridDim.x * kRowThreads) {
-    double o[LD];
+  for (int m0 = blockIdx.x * (kRowThreads * ROWS) + threadIdx.x; m0 < M; m0 += gridDim.x * (kRowThreads * ROWS)) {
+    double o[ROWS][LD];
+    int mr[ROWS];
 #pragma unroll
-    for (int c = 0; c < LD / 4; ++c) {
-      const double4_t v = ldg256(own_run + (size_t)m * LD + 4 * c);
-      o[4 * c] = v.x; o[4 * c + 1] = v.y; o[4 * c + 2] = v.z; o[4 * c + 3] = v.w;
+    for (int j = 0; j < ROWS; ++j) {
+      mr[j] = m0 + j * kRowThreads;
+      const int mc = mr[j] < M ? mr[j] : m0;                 // rows past the end recompute row m0
+#pragma unroll
+      for (int c = 0; c < LD / 4; ++c) {
+        const double4_t v = ldg256(own_run + (size_t)mc * LD + 4 * c);
+        o[j][4 * c] = v.x; o[j][4 * c + 1] = v.y; o[j][4 * c + 2] = v.z; o[j][4 * c + 3] = v.w;
+      }
     }
-    double* wrow = w_run + (size_t)m * RNB;
     for (int ob = 0; ob < RNB; ob += 4) {
-      double4_t acc{0.0, 0.0, 0.0, 0.0};
+      double4_t acc[ROWS];
+#pragma unroll
+      for (int j = 0; j < ROWS; ++j) acc[j] = double4_t{0.0, 0.0, 0.0, 0.0};
 #pragma unroll
       for (int a = 0; a < LD; ++a) {
         const double4_t p = lds32(Ps + a * RNB + ob);
-        acc.x = fma(o[a], p.x, acc.x); acc.y = fma(o[a], p.y, acc.y);
-        acc.z = fma(o[a], p.z, acc.z); acc.w = fma(o[a], p.w, acc.w);
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+          acc[j].x = fma(o[j][a], p.x, acc[j].x); acc[j].y = fma(o[j][a], p.y, acc[j].y);
+          acc[j].z = fma(o[j][a], p.z, acc[j].z); acc[j].w = fma(o[j][a], p.w, acc[j].w);
+        }
       }
-      stg256(wrow + ob, acc);
+#pragma unroll
+      for (int j = 0; j < ROWS; ++j)
+        if (mr[j] < M) stg256(w_run + (size_t)mr[j] * RNB + ob, acc[j]);
     }
   }
 }
 
-template <int LD>
+template <int LD, int ROWS>
 __global__ void __launch_bounds__(kRowThreads) row_n_kernel(const double* __restrict__ G,
                                                             const double* __restrict__ pn,
                                                             const double* __restrict__ own,
@@ -259,32 +273,49 @@ __global__ void __launch_bounds__(kRowThreads) row_n_kernel(const double* __rest
   const double* g_run = G + (size_t)run * M * RNB;
   const double* own_run = own + (size_t)run * M * LD;
   double* out_run = out + (size_t)run * M * LD;
-  for (int m = blockIdx.x * kRowThreads + threadIdx.x; m < M; m += gridDim.x * kRowThreads) {
-    double acc[LD];
+  for (int m0 = blockIdx.x * (kRowThreads * ROWS) + threadIdx.x; m0 < M; m0 += gridDim.x * (kRowThreads * ROWS)) {
+    double acc[ROWS][LD];
+    int mr[ROWS];
+    const double* grow[ROWS];
 #pragma unroll
-    for (int a = 0; a < LD; ++a) acc[a] = 0.0;
-    const double* grow = g_run + (size_t)m * RNB;
+    for (int j = 0; j < ROWS; ++j) {
+      mr[j] = m0 + j * kRowThreads;
+      grow[j] = g_run + (size_t)(mr[j] < M ? mr[j] : m0) * RNB;   // rows past the end recompute row m0
+#pragma unroll
+      for (int a = 0; a < LD; ++a) acc[j][a] = 0.0;
+    }
     for (int ob = 0; ob < RNB; ob += 4) {
-      const double4_t gq = ldg256(grow + ob);
-      const double gv[4] = {gq.x, gq.y, gq.z, gq.w};
+      double gv[ROWS][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < ROWS; ++j) {
+        const double4_t gq = ldg256(grow[j] + ob);
+        gv[j][0] = gq.x; gv[j][1] = gq.y; gv[j][2] = gq.z; gv[j][3] = gq.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
 #pragma unroll
         for (int c = 0; c < LD / 4; ++c) {
-          const double4_t p = lds32(Ps + (ob + j) * LD + 4 * c);
-          acc[4 * c] = fma(gv[j], p.x, acc[4 * c]);         acc[4 * c + 1] = fma(gv[j], p.y, acc[4 * c + 1]);
-          acc[4 * c + 2] = fma(gv[j], p.z, acc[4 * c + 2]); acc[4 * c + 3] = fma(gv[j], p.w, acc[4 * c + 3]);
+          const double4_t p = lds32(Ps + (ob + i) * LD + 4 * c);
+#pragma unroll
+          for (int j = 0; j < ROWS; ++j) {
+            acc[j][4 * c] = fma(gv[j][i], p.x, acc[j][4 * c]);         acc[j][4 * c + 1] = fma(gv[j][i], p.y, acc[j][4 * c + 1]);
+            acc[j][4 * c + 2] = fma(gv[j][i], p.z, acc[j][4 * c + 2]); acc[j][4 * c + 3] = fma(gv[j][i], p.w, acc[j][4 * c + 3]);
+          }
         }
       }
     }
-    double d = 1.0;
-    if (normalize) d = (double)max(__ldg(deg + m), 1);
 #pragma unroll
-    for (int c = 0; c < LD / 4; ++c) {
-      const double4_t ov = ldg256(own_run + (size_t)m * LD + 4 * c);
-      double4_t v{acc[4 * c] * ov.x, acc[4 * c + 1] * ov.y, acc[4 * c + 2] * ov.z, acc[4 * c + 3] * ov.w};
-      if (normalize) { v.x = v.x / d; v.y = v.y / d; v.z = v.z / d; v.w = v.w / d; }
-      stg256(out_run + (size_t)m * LD + 4 * c, v);
+    for (int j = 0; j < ROWS; ++j) {
+      if (mr[j] >= M) continue;
+      double d = 1.0;
+      if (normalize) d = (double)max(__ldg(deg + mr[j]), 1);
+#pragma unroll
+      for (int c = 0; c < LD / 4; ++c) {
+        const double4_t ov = ldg256(own_run + (size_t)mr[j] * LD + 4 * c);
+        double4_t v{acc[j][4 * c] * ov.x, acc[j][4 * c + 1] * ov.y, acc[j][4 * c + 2] * ov.z, acc[j][4 * c + 3] * ov.w};
+        if (normalize) { v.x = v.x / d; v.y = v.y / d; v.z = v.z / d; v.w = v.w / d; }
+        stg256(out_run + (size_t)mr[j] * LD + 4 * c, v);
+      }
     }
   }
 }
@@ -566,11 +597,16 @@ static int launch_gemm(GemmArgs g, int n_runs, cudaStream_t st) {
 static int launch_w(const double* own, const double* pw, double* W, int M, int LD, int RNB, int n_runs,
                     cudaStream_t st) {
   const size_t smem = (size_t)LD * RNB * 8;
-  const int gx = min((M + kRowThreads - 1) / kRowThreads, 148 * 2);
+  const int rows_env = env_int("MMSBM_ROWS", 2);
 #define MMSBM_ROW_W(LDv)                                                                        \
   if (LD == LDv && smem <= 200 * 1024) {                                                        \
-    MMSBM_CUDA(cudaFuncSetAttribute(row_w_kernel<LDv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    row_w_kernel<LDv><<<dim3(gx, n_runs), kRowThreads, smem, st>>>(own, pw, W, M, RNB);         \
+    constexpr int kRows = (LDv <= 24) ? 2 : 1;   /* 2 x LD operand registers per lane */          \
+    const bool two = kRows == 2 && rows_env == 2;                                               \
+    auto kern = two ? row_w_kernel<LDv, kRows> : row_w_kernel<LDv, 1>;                          \
+    const int per = kRowThreads * (two ? 2 : 1);                                                \
+    const int gx = min((M + per - 1) / per, 148 * 2);                                           \
+    MMSBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<dim3(gx, n_runs), kRowThreads, smem, st>>>(own, pw, W, M, RNB);                      \
     MMSBM_LAUNCH_CHECK("row_w_kernel");                                                         \
     return 0;                                                                                   \
   }
@@ -584,11 +620,17 @@ static int launch_w(const double* own, const double* pw, double* W, int M, int L
 static int launch_n(const double* G, const double* pn, const double* own, const int32_t* deg, double* out,
                     int M, int LD, int RNB, int normalize, int n_runs, cudaStream_t st) {
   const size_t smem = (size_t)LD * RNB * 8;
-  const int gx = min((M + kRowThreads - 1) / kRowThreads, 148 * 2);
+  // one row per lane here: two rows cost occupancy (142 registers) and measured slower
+  const int rows_env = env_int("MMSBM_ROWS_N", 1);
 #define MMSBM_ROW_N(LDv)                                                                        \
   if (LD == LDv && smem <= 200 * 1024) {                                                        \
-    MMSBM_CUDA(cudaFuncSetAttribute(row_n_kernel<LDv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    row_n_kernel<LDv><<<dim3(gx, n_runs), kRowThreads, smem, st>>>(G, pn, own, deg, out, M, RNB, normalize); \
+    constexpr int kRows = (LDv <= 24) ? 2 : 1;   /* 2 x LD accumulator registers per lane */      \
+    const bool two = kRows == 2 && rows_env == 2;                                               \
+    auto kern = two ? row_n_kernel<LDv, kRows> : row_n_kernel<LDv, 1>;                          \
+    const int per = kRowThreads * (two ? 2 : 1);                                                \
+    const int gx = min((M + per - 1) / per, 148 * 2);                                           \
+    MMSBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<dim3(gx, n_runs), kRowThreads, smem, st>>>(G, pn, own, deg, out, M, RNB, normalize); \
     MMSBM_LAUNCH_CHECK("row_n_kernel");                                                         \
     return 0;                                                                                   \
   }
