@@ -4,8 +4,17 @@ Same observable behaviour as the reference's DataHandler (src/data_handler.py:10
 every cell is ``str()``-ed, ids are ranked by ``sorted(set(strings))`` (lexicographic:
 '10' < '2'), train rows are encoded to an int64 ``[N,3]`` array, test rows whose
 user / item / rating was not seen in training are dropped with a warning, and fitted
-parameters are decoded back to the original labels.  The python-level ``str`` runs
-once per DISTINCT value, not once per cell; the result is identical.
+parameters are decoded back to the original labels.
+
+Fast path: a column is first factorised on its RAW values (one hash
+pass, ``pd.factorize``), ``str()`` then runs once per DISTINCT value, the distinct strings are
+ranked, and the codes are mapped through that small table -- O(N) numpy work plus O(D log D)
+python work instead of N python-level ``str`` / dict operations.  It is taken only where it
+is provably identical to ``sorted(set(str(x) for x in column.tolist()))``: integer, bool and
+float dtypes (floats factorised on their bit patterns, so -0.0 / 0.0 stay distinct like
+their strings; distinct raw values with equal strings are merged by the string table) and
+object columns that hold only ``str``.  Anything else (mixed objects, nullable / datetime
+dtypes, frames that do not have exactly three columns) takes the per-cell path.
 """
 import logging
 
@@ -26,6 +35,29 @@ def _stringify(col):
         table = np.array([str(v) for v in uniq.tolist()], dtype=object)
         return table[inv]
     return np.array([str(x) for x in values], dtype=object)
+
+
+def _distinct_strings(col):
+    """``(codes, strings)`` of a pandas column: ``strings[codes[n]] == str(col.tolist()[n])`` for
+    every row.  ``strings`` may hold duplicates (two raw values that print alike); callers go
+    through a string-keyed table, which merges them."""
+    arr = col.to_numpy()
+    kind = arr.dtype.kind
+    if kind in "iub":
+        codes, uniq = pd.factorize(arr)
+        return codes, [str(v) for v in uniq.tolist()]
+    if kind == "f" and arr.dtype.itemsize in (4, 8):
+        bits = np.ascontiguousarray(arr).view(np.int32 if arr.dtype.itemsize == 4 else np.int64)
+        codes, ubits = pd.factorize(bits)
+        return codes, [str(v) for v in ubits.view(arr.dtype).tolist()]
+    if kind == "O" and len(arr) and pd.api.types.infer_dtype(arr, skipna=False) == "string":
+        codes, uniq = pd.factorize(arr)
+        return codes, [str(v) for v in uniq.tolist()]
+    values = np.array([str(x) for x in col.tolist()], dtype=object)      # per-cell path
+    if not len(values):
+        return np.zeros(0, dtype=np.int64), []
+    codes, uniq = pd.factorize(values)
+    return codes, uniq.tolist()
 
 
 def _rank_table(strings):
@@ -107,9 +139,22 @@ class DataHandler:
         return {inv[a]: pd.DataFrame(pr[:, :, a]) for a in range(pr.shape[2])}
 
     def format_train_data(self, data):
-        data = self._to_object_str(data)
-        self._check_data(data)
-        return self.parse_train_data(data)
+        if data.shape[1] != 3:                   # the reference's behaviour for odd frames, cell by cell
+            data = self._to_object_str(data)
+            self._check_data(data)
+            return self.parse_train_data(data)
+        # (_check_data runs on the stringified frame in the reference, src/data_handler.py:103-105,
+        #  where no cell is null any more: it cannot fire, so there is nothing to check here)
+        out = np.empty((len(data), 3), dtype=np.int64)
+        tables = []
+        for c in range(3):
+            codes, strings = _distinct_strings(data.iloc[:, c])
+            table = {s: k for k, s in enumerate(sorted(set(strings)))}
+            lut = np.array([table[s] for s in strings], dtype=np.int64)
+            out[:, c] = lut[codes] if len(codes) else 0
+            tables.append(table)
+        self.obs_dict, self.items_dict, self.ratings_dict = tables
+        return out
 
     def _check_test_in_train(self, data):
         """Column by column (users, items, ratings -- looked up BY NAME like the
@@ -128,10 +173,30 @@ class DataHandler:
         return data
 
     def format_test_data(self, data):
-        data = self._to_object_str(data)
-        self._check_data(data)
-        data = self._check_test_in_train(data)
-        return self.parse_test_data(data)
+        if list(data.columns) != ["users", "items", "ratings"]:
+            # the reference looks the columns up by name (KeyError otherwise) and encodes by position
+            data = self._to_object_str(data)
+            self._check_data(data)
+            data = self._check_test_in_train(data)
+            return self.parse_test_data(data)
+        logger = logging.getLogger("MMSBM")
+        alive = np.ones(len(data), dtype=bool)
+        enc = np.empty((len(data), 3), dtype=np.int64)
+        for c, (column, table) in enumerate((("users", self.obs_dict), ("items", self.items_dict),
+                                             ("ratings", self.ratings_dict))):
+            codes, strings = _distinct_strings(data[column])
+            lut = np.array([table.get(s, -1) for s in strings], dtype=np.int64)
+            present = np.zeros(len(strings), dtype=bool)
+            present[codes[alive]] = True                      # distinct values among the rows still there
+            unseen = set(s for s, p, k in zip(strings, present, lut) if p and k < 0)
+            if len(unseen):
+                logger.warning(
+                    f"The {column} {', '.join(str(a) for a in unseen)} are in the test set but weren't in "
+                    f"the train set so I'll remove them.")
+                bad = np.array([s in unseen for s in strings], dtype=bool)
+                alive &= ~bad[codes]
+            enc[:, c] = lut[codes] if len(codes) else 0
+        return enc[alive]
 
     def return_dicts(self):
         return self.obs_dict, self.items_dict, self.ratings_dict

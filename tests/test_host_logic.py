@@ -155,3 +155,20 @@ def test_shard_runs_and_user_partition():
     b = user_partition(deg, 2)
     left = deg[:b[1]].sum()
     assert abs(left - deg.sum() / 2) <= deg.max()
+
+
+@pytest.mark.parametrize("case", ["int", "float", "str", "bool", "mixed", "dates", "nan"])
+def test_encoding_fast_path_matches_reference_for_every_dtype(golden_dir, case):
+    """The factorise-first encoding (data_handler._distinct_strings) against outputs of the real
+    reference DataHandler (tests/golden/make_golden_encoding.py) and against the per-cell path."""
+    from tests.util import dtype_frames
+    g = np.load(os.path.join(golden_dir, "encoding_dtypes.npz"))
+    dicts = json.load(open(os.path.join(golden_dir, "encoding_dtypes.json")))[case]
+    train, test = dtype_frames()[case]
+    dh = DataHandler()
+    np.testing.assert_array_equal(dh.format_train_data(train.copy()), g[case + "_train"])
+    assert [[list(kv) for kv in d.items()] for d in dh.return_dicts()] == dicts      # same keys, same order
+    np.testing.assert_array_equal(dh.format_test_data(test.copy()), g[case + "_test"])
+    slow = DataHandler()
+    np.testing.assert_array_equal(slow.parse_train_data(slow._to_object_str(train.copy())), g[case + "_train"])
+    assert slow.return_dicts() == dh.return_dicts()

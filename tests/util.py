@@ -44,3 +44,41 @@ def rel_err(a, b):
     north_star tolerance (1e-10) is stated in."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))) if a.size else 0.0
+
+
+def dtype_frames(seed=1, n=3000):
+    """(train, test) frames per column-dtype case for the encoding tests: integer, float (with
+    -0.0 / inf / float32), str, bool / small ints, mixed python objects / nullable / categorical,
+    datetimes, NaN.  Each test frame holds a sample of the train rows plus rows with unseen ids."""
+    g = np.random.default_rng(seed)
+    cases = {
+        "int": pd.DataFrame({"users": g.integers(-50, 300, n), "items": g.integers(0, 120, n),
+                             "ratings": g.integers(1, 6, n)}),
+        "float": pd.DataFrame({"users": g.integers(0, 300, n).astype(float),
+                               "items": g.choice([0.0, -0.0, 1.5, 2.25, 1e20, np.inf], n),
+                               "ratings": g.choice([0.5, 1.0, 1.5], n).astype(np.float32)}),
+        "str": pd.DataFrame({"users": ["u%d" % x for x in g.integers(0, 300, n)],
+                             "items": ["%d" % x for x in g.integers(0, 120, n)],
+                             "ratings": [str(x) for x in g.integers(1, 6, n)]}),
+        "bool": pd.DataFrame({"users": g.integers(0, 2, n).astype(bool), "items": g.integers(0, 120, n).astype(np.uint8),
+                              "ratings": g.integers(1, 6, n).astype(np.int16)}),
+        "mixed": pd.DataFrame({"users": pd.Series(g.choice(np.array([1, 1.0, True, "1", "a", 2, 2.5], dtype=object), n),
+                                                  dtype=object),
+                               "items": pd.Series(g.integers(0, 50, n)).astype("Int64"),
+                               "ratings": pd.Categorical(g.choice(["lo", "mid", "hi"], n))}),
+        "dates": pd.DataFrame({"users": pd.to_datetime(g.integers(0, 40, n), unit="D"),
+                               "items": g.integers(0, 30, n), "ratings": g.integers(1, 4, n)}),
+        "nan": pd.DataFrame({"users": g.choice([1.0, np.nan, 3.0], n), "items": g.integers(0, 30, n),
+                             "ratings": g.integers(1, 4, n)}),
+    }
+    out = {}
+    for name, d in cases.items():
+        extra = d.iloc[:3].copy()
+        if name == "str":
+            extra.iloc[0, 1] = "100000"                       # an item that is not in the train set
+        elif name == "bool":
+            extra.iloc[0, 1] = 200                            # items are 0..119 (uint8)
+        elif name != "mixed":
+            extra.iloc[0, 1] = extra.iloc[0, 1] + 100000
+        out[name] = (d, pd.concat([d.iloc[::7], extra]))
+    return out
