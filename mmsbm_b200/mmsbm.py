@@ -251,8 +251,18 @@ class MMSBM:
         (src/mmsbm.py:415-439): per user (groups in sorted key order) up to items_per_fold
         held-out rows, drawn from ``self.rng`` in that order; index label 0 is never held out
         (the reference filters str(a) != "0", :435).  The fits do not touch ``self.rng``, so
-        building all folds first consumes it exactly as the reference's interleaved loop."""
+        building all folds first consumes it exactly as the reference's interleaved loop.
+
+        Fast path: ``rng.choice(x.index, k, replace=False)`` draws
+        positions from the group SIZE only, so the same stream is consumed by
+        ``rng.choice(len(x), k, replace=False)`` on row positions kept in numpy arrays -- no
+        pandas groupby / .loc / .isin per fold.  Taken when the frame has a unique index and a
+        plain integer / float-without-NaN / str user column (where ``np.unique`` orders the
+        groups exactly like ``groupby``); anything else goes through pandas as before."""
         items_per_fold = structure_folds(data, folds)
+        fast = self._make_folds_fast(data, folds, items_per_fold)
+        if fast is not None:
+            return fast
         temp = data
         pairs = []
         for _ in range(folds):
@@ -265,6 +275,43 @@ class MMSBM:
             train = data[~data.index.isin(test.index)]
             temp = temp[~temp.index.isin(test_indices)]
             pairs.append((train, test))
+        return pairs
+
+    def _make_folds_fast(self, data, folds, items_per_fold):
+        if not data.index.is_unique or items_per_fold <= 0:
+            return None
+        users = data.iloc[:, 0].to_numpy()
+        kind = users.dtype.kind
+        if kind == "f" and np.isnan(users).any():
+            return None
+        if kind == "O":
+            import pandas as pd
+            if not len(users) or pd.api.types.infer_dtype(users, skipna=False) != "string":
+                return None
+        elif kind not in "iuf":
+            return None
+        _, codes = np.unique(users, return_inverse=True)           # sorted keys, like groupby
+        order = np.argsort(codes, kind="stable")                   # rows of a group in frame order
+        bounds = np.flatnonzero(np.diff(codes[order], prepend=-1, append=codes.max(initial=-1) + 1))
+        groups = [order[bounds[j]:bounds[j + 1]] for j in range(len(bounds) - 1)]
+        labels = data.index
+        zero_label = np.fromiter((str(a) == "0" for a in labels), dtype=bool, count=len(labels)) \
+            if labels.dtype.kind not in "iu" else (labels.to_numpy() == 0)
+        alive = np.ones(len(data), dtype=bool)
+        pairs = []
+        for _ in range(folds):
+            picked = []
+            for rows in groups:
+                rows = rows[alive[rows]]
+                take = min(items_per_fold, len(rows))
+                if take > 0:
+                    picked.append(rows[self.rng.choice(len(rows), take, replace=False)])
+            picked = np.concatenate(picked) if picked else np.zeros(0, dtype=np.int64)
+            picked = picked[~zero_label[picked]]
+            held = np.zeros(len(data), dtype=bool)
+            held[picked] = True
+            pairs.append((data.iloc[~held], data.iloc[picked]))
+            alive[picked] = False
         return pairs
 
     def cv_fit(self, data, folds=5):

@@ -172,3 +172,26 @@ def test_encoding_fast_path_matches_reference_for_every_dtype(golden_dir, case):
     slow = DataHandler()
     np.testing.assert_array_equal(slow.parse_train_data(slow._to_object_str(train.copy())), g[case + "_train"])
     assert slow.return_dicts() == dh.return_dicts()
+
+
+@pytest.mark.parametrize("case", ["fixture", "ints", "strs", "shuffled_index", "str_index", "floats"])
+def test_fold_construction_matches_reference(golden_dir, case):
+    """MMSBM._make_folds (numpy fast path and the pandas path) against the folds the real
+    reference's cv_fit builds (tests/golden/make_golden_folds.py): same held-out labels in the
+    same order, same train rows, and the generator left in the same state."""
+    import hashlib
+    from mmsbm_b200.mmsbm import MMSBM
+    from tests.util import fold_frames
+    want = json.load(open(os.path.join(golden_dir, "folds.json")))[case]
+    frame, folds = fold_frames()[case]
+    for fast in (True, False):
+        m = MMSBM(2, 2, iterations=1, seed=7)
+        if not fast:
+            m._make_folds_fast = lambda *a: None
+        pairs = m._make_folds(frame, folds)
+        if fast:
+            assert MMSBM._make_folds_fast(MMSBM(2, 2, seed=7), frame, folds, structure_folds(frame, folds)) is not None
+        assert [[str(a) for a in te.index] for _, te in pairs] == want["test"]
+        assert [hashlib.sha1(",".join(str(a) for a in tr.index).encode()).hexdigest() for tr, _ in pairs] \
+            == want["train_sha1"]
+        assert float(m.rng.random()) == want["next_random"]

@@ -82,3 +82,23 @@ def dtype_frames(seed=1, n=3000):
             extra.iloc[0, 1] = extra.iloc[0, 1] + 100000
         out[name] = (d, pd.concat([d.iloc[::7], extra]))
     return out
+
+
+def fold_frames(seed=0):
+    """(frame, folds) cases for the fold-construction tests: the reference fixture, integer / str /
+    float users, a shuffled index and an index of strings that contains the label "0"."""
+    g = np.random.default_rng(seed)
+    n = 6000
+    return {
+        "fixture": (mock_data(1), 2),
+        "ints": (pd.DataFrame({"users": g.integers(0, 300, n), "items": g.integers(0, 40, n),
+                               "ratings": g.integers(1, 6, n)}), 5),
+        "strs": (pd.DataFrame({"users": ["u%d" % x for x in g.integers(0, 300, n)], "items": g.integers(0, 23, n),
+                               "ratings": g.integers(1, 6, n)}), 4),
+        "shuffled_index": (pd.DataFrame({"users": g.integers(0, 50, 2000), "items": g.integers(0, 30, 2000),
+                                         "ratings": g.integers(1, 6, 2000)}).sample(frac=1.0, random_state=3), 3),
+        "str_index": (pd.DataFrame({"users": g.integers(0, 50, 500), "items": g.integers(0, 12, 500),
+                                    "ratings": g.integers(1, 6, 500)}, index=[str(i) for i in range(500)]), 3),
+        "floats": (pd.DataFrame({"users": g.integers(0, 50, 2000).astype(float), "items": g.integers(0, 30, 2000),
+                                 "ratings": g.integers(1, 6, 2000)}), 3),
+    }
