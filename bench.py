@@ -19,12 +19,15 @@ runs (``sampling``) over the same synthetic ratings.
             iteration): algorithmic bytes B_alg*N*S / their CUDA-event
             time (mmsbm_em_step_profiled), against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline  the oracle port (numpy restatement of the reference) on the host, one
-            thread, on a bounded row sample of the same shape.
+            thread, on a bounded row sample of the same shape; cpu_baseline_numba = the numba
+            port (oracle/mmsbm_oracle_numba.py, the backend the reference picks by itself on a
+            CPU host), all host threads, same sample.
 
 N > 1 (torchrun): independent runs shard over ranks with no data-path collective; every
 rank processes S runs of its own seeds over a replica of the ratings (weak scaling).
 ``--impl reference`` times the reference's CPU algorithm (oracle port; the reference is
-pure Python and cannot travel) with one process per run, as its spawn pool does.
+pure Python and cannot travel) with one process per run, as its spawn pool does; the numba
+port by default (``--cpu-backend``), host cores split evenly between the processes.
 """
 import argparse
 import ctypes
@@ -168,15 +171,47 @@ def cpu_baseline_port(U, I, K, L, n_rows, repeats=3):
                       f"kernels_numpy.update_coefficients)"}
 
 
+def cpu_baseline_numba(U, I, K, L, n_rows, repeats=3):
+    """Numba port (the backend the reference's load_backend("auto") picks on a host without
+    CuPy), all host threads in its parallel omega phase, one EM iteration of one run."""
+    try:
+        import numba
+        from oracle import mmsbm_oracle as orc, mmsbm_oracle_numba as onb
+    except ImportError as e:        # numba missing on this host: say so instead of guessing
+        return {"unavailable": str(e)}
+    data = _cpu_sample(U, I, K, L, n_rows)
+    fu, fi = orc.degree_factors(data, K, L)
+    th, et, pr = (a[0] for a in seeded_inits(data, U, I, K, L, [1]))
+    onb.em_iteration(data[:2000], th, et, pr, fu, fi)             # JIT compile outside the timing
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        onb.em_iteration(data, th, et, pr, fu, fi)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": data.shape[0] / best, "unit": "rating-updates/s", "cores": int(numba.get_num_threads()),
+            "kind": "port",
+            "sample": f"{data.shape[0]} rows of the same U/I/K/L, 1 run, 1 EM iteration incl. the three "
+                      f"normalisations, best of {repeats}, JIT excluded; oracle/mmsbm_oracle_numba.py "
+                      f"(restatement of kernels_numba.update_coefficients: parallel omega phase, serial scatter)"}
+
+
 _W = {}
 
 
-def _ref_worker_init(U, I, K, L, n_rows):
+def _ref_worker_init(U, I, K, L, n_rows, backend, threads):
     from oracle import mmsbm_oracle as orc
     data = _cpu_sample(U, I, K, L, n_rows)
     _W["orc"], _W["data"] = orc, data
     _W["f"] = orc.degree_factors(data, K, L)
     _W["shape"] = (U, I, K, L)
+    _W["step"] = lambda th, et, pr: orc.em_iteration(data, th, et, pr, *_W["f"], chunk=50_000)
+    if backend == "numba":
+        import numba
+        from oracle import mmsbm_oracle_numba as onb
+        numba.set_num_threads(max(1, min(threads, numba.config.NUMBA_NUM_THREADS)))
+        _W["step"] = lambda th, et, pr: onb.em_iteration(data, th, et, pr, *_W["f"])
+        th, et, pr = (a[0] for a in seeded_inits(data, U, I, K, L, [0]))
+        onb.em_iteration(data[:2000], th, et, pr, *_W["f"])       # JIT compile in the initializer
 
 
 def _ref_worker_step(args):
@@ -185,7 +220,7 @@ def _ref_worker_step(args):
     U, I, K, L = _W["shape"]
     th, et, pr = (a[0] for a in seeded_inits(data, U, I, K, L, [seed]))
     for _ in range(iters):
-        th, et, pr = orc.em_iteration(data, th, et, pr, *_W["f"], chunk=50_000)
+        th, et, pr = _W["step"](th, et, pr)
     return float(th.sum())
 
 
@@ -198,10 +233,20 @@ def run_reference_arm(args, shape):
         return
     U, I, N, K, L, S = shape
     n_rows = max(args.cpu_rows, max(U, I))
-    procs = min(S, os.cpu_count() or 1)
+    cores = os.cpu_count() or 1
+    procs = min(S, cores)
     iters = 1
-    ctx = mp.get_context("fork")
-    with ctx.Pool(processes=procs, initializer=_ref_worker_init, initargs=(U, I, K, L, n_rows)) as pool:
+    backend = args.cpu_backend
+    if backend == "auto":           # the reference's own order on a CPU host: numba, then numpy
+        try:
+            import numba  # noqa: F401
+            backend = "numba"
+        except ImportError:
+            backend = "numpy"
+    threads = max(1, cores // procs) if backend == "numba" else 1
+    ctx = mp.get_context("spawn" if backend == "numba" else "fork")   # numba's thread pool does not survive fork
+    with ctx.Pool(processes=procs, initializer=_ref_worker_init,
+                  initargs=(U, I, K, L, n_rows, backend, threads)) as pool:
         for _ in range(args.warmup):
             pool.map(_ref_worker_step, [(s, iters) for s in range(S)])
         t0 = time.perf_counter()
@@ -210,7 +255,8 @@ def run_reference_arm(args, shape):
         dt = time.perf_counter() - t0
     value = n_rows * iters * S * args.steps / dt
     sample = (f"{n_rows} rows of the {args.workload} shape (same U/I/K/L/R), {S} runs x {iters} EM iteration per "
-              f"step, one process per run ({procs} processes), init included")
+              f"step, one process per run ({procs} processes x {threads} thread(s), {cores} host cores), "
+              f"{backend} port of the reference kernels, init included")
     line = {
         "impl": "reference", "metric": "rating-updates/sec", "value": value, "unit": "rating-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -218,8 +264,8 @@ def run_reference_arm(args, shape):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "users": U, "items": I, "ratings": N, "K": K, "L": L, "R": R,
                    "sampling": S, "cpu_sample_rows": n_rows},
-        "cpu_baseline": {"value": value, "unit": "rating-updates/s", "cores": procs, "kind": "port",
-                         "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "rating-updates/s", "cores": procs * threads, "kind": "port",
+                         "backend": backend, "sample": sample},
         "e2e": {"value": value, "unit": "rating-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -395,9 +441,10 @@ def run_b200_arm(args, shape):
                       f"{T} EM iterations, likelihood, D2H theta/eta/pr/likelihood",
                "likelihood_run0": float(lik[0])}
 
-    cpu = None
+    cpu = cpu_nb = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline_port(U, I, K, L, args.cpu_rows)
+        cpu_nb = cpu_baseline_numba(U, I, K, L, args.cpu_rows)
 
     if rank == 0:
         line = {
@@ -411,7 +458,8 @@ def run_b200_arm(args, shape):
                        "parallelism": f"runs sharded over {world} GPU(s), no data-path collective",
                        "l2": "no explicit flush: one iteration touches the parameters of all runs and both "
                              "index arrays (> 126 MB L2 at ml20m); see DESIGN.md"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_numba": cpu_nb, "e2e": e2e,
+            "gpu_launches": int(launches),
             "clocks": clk, "index_build_ms": build_ms, "host_datagen_s": gen_s,
             "ms_per_iteration": ms / args.steps / T,
         }
@@ -429,6 +477,8 @@ def main():
     ap.add_argument("--workload", default="ml20m", choices=sorted(WORKLOADS))
     ap.add_argument("--iters-per-step", type=int, default=400)
     ap.add_argument("--cpu-rows", type=int, default=200_000)
+    ap.add_argument("--cpu-backend", default="auto", choices=["auto", "numba", "numpy"],
+                    help="--impl reference: which port of the reference kernels to time")
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--shard", default="runs", choices=["runs", "ratings"],
                     help="N > 1 only: shard independent runs (default, weak scaling) or the ratings of "

@@ -48,6 +48,33 @@ class Engine:
             del raw
             self._build_graph()
 
+    @classmethod
+    def for_prediction(cls, n_users, n_items, n_levels, K, L, device=None):
+        """An engine without a training set: holds parameters (``set_params``) and serves
+        ``prod_dist_device`` / ``mean_over_runs`` -- what a model restored by ``MMSBM.load``
+        needs for ``predict``.  ``run`` / ``likelihood`` need the ratings and refuse."""
+        self = cls.__new__(cls)
+        self.lib = _lib.load(require_device=True)
+        if not torch.cuda.is_available():
+            raise ImportError("mmsbm_b200: torch sees no CUDA device; there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        self.N = 0
+        self.U, self.I, self.R, self.K, self.L = int(n_users), int(n_items), int(n_levels), int(K), int(L)
+        self.ldk, self.ldl = self.lib.mmsbm_row_stride(self.K), self.lib.mmsbm_row_stride(self.L)
+        self.S = 0
+        self.theta = self.eta = self.pr = None
+        self._alt = None
+        self._ws = None
+        self.cols = None
+        self.useg = None                          # no index structure
+        return self
+
+    def _need_ratings(self):
+        if getattr(self, "useg", None) is None:
+            raise RuntimeError("this engine holds parameters only (restored model): "
+                               "fit again to iterate or to compute a likelihood")
+
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -123,6 +150,9 @@ class Engine:
         alt_flat, alt_eta, alt_pr = pair(None, None)
         self._alt = (torch.empty_like(self.theta), alt_eta, alt_pr)
         self._alt_flat = alt_flat
+        if getattr(self, "useg", None) is None:   # prediction-only engine: no EM workspace
+            self._ws, self._ws_bytes = None, 0
+            return
         need = _lib.C.c_size_t(0)
         _lib.check(self.lib.mmsbm_em_workspace_bytes(self.N, self.U, self.I, self.R, self.K, self.L, S,
                                                      _lib.C.byref(need)), "em_workspace_bytes")
@@ -140,6 +170,7 @@ class Engine:
         """``iterations`` EM steps for all S runs, asynchronous on the current stream."""
         if iterations <= 0:
             return
+        self._need_ratings()
         a = (self.theta, self.eta, self.pr)
         b = self._alt
         _lib.check(self.lib.mmsbm_em_run(
@@ -153,6 +184,7 @@ class Engine:
     def step_raw(self, flags):
         """One step into the alternate buffers with ``flags`` (RAW_THETA / RAW_ETA_PR);
         returns the three output tensors without swapping."""
+        self._need_ratings()
         b = self._alt
         _lib.check(self.lib.mmsbm_em_step(
             *self._graph_args(), self.N, self.U, self.I, self.R, self.K, self.L, self.S,
@@ -174,6 +206,7 @@ class Engine:
 
     # ---------------------------------------------------------------- reductions
     def likelihood_device(self):
+        self._need_ratings()
         out = self._empty(self.S, torch.float64)
         need = _lib.C.c_size_t(0)
         _lib.check(self.lib.mmsbm_likelihood_workspace_bytes(self.U, self.S, _lib.C.byref(need)),

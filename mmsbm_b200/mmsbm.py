@@ -366,6 +366,51 @@ class MMSBM:
         self.logger.info(f"They have mean {np.mean(accuracies)} and sd {np.std(accuracies)}.")
         return accuracies
 
+    # ------------------------------------------------------------------ save / load
+    def save(self, path):
+        """Write the fitted model to one ``.npz`` file: the parameters and likelihood of every run,
+        the three id dictionaries and the constructor arguments.  (The reference has no on-disk
+        format; this is the adjacent feature of SURVEY.md section 8 f4.)  ``MMSBM.load(path)``
+        gives a model that can ``predict`` and ``score``."""
+        import json
+        self._check_is_fitted()
+        config = {"user_groups": self.user_groups, "item_groups": self.item_groups,
+                  "iterations": self.iterations, "sampling": self.sampling, "debug": self.debug,
+                  "backend": self.backend, "shard": self.shard}
+        dicts = [list(d.items()) for d in self.data_handler.return_dicts()]
+        with open(path, "wb") as fh:
+            np.savez_compressed(
+                fh, format_version=np.int64(1), config=np.array(json.dumps(config)),
+                dicts=np.array(json.dumps(dicts)),
+                theta=np.stack([a["theta"] for a in self.results]),
+                eta=np.stack([a["eta"] for a in self.results]),
+                pr=np.stack([a["pr"] for a in self.results]),
+                likelihood=np.array([a["likelihood"] for a in self.results], dtype=np.float64))
+
+    @classmethod
+    def load(cls, path):
+        """Restore a model written by ``save`` (prediction side only: no training rows are kept)."""
+        import json
+        with np.load(path, allow_pickle=False) as z:
+            if int(z["format_version"]) != 1:
+                raise ValueError(f"unknown mmsbm_b200 model format {int(z['format_version'])}")
+            config = json.loads(str(z["config"]))
+            dicts = [dict((k, int(v)) for k, v in d) for d in json.loads(str(z["dicts"]))]
+            theta, eta, pr, lik = z["theta"], z["eta"], z["pr"], z["likelihood"]
+        self = cls(**config)
+        self.data_handler = DataHandler()
+        self.data_handler.obs_dict, self.data_handler.items_dict, self.data_handler.ratings_dict = dicts
+        self.results = [{"likelihood": np.float64(lik[s]), "pr": pr[s], "theta": theta[s], "eta": eta[s]}
+                        for s in range(theta.shape[0])]
+        self.p, self.m = theta.shape[1] - 1, eta.shape[1] - 1
+        self.ratings = list(range(pr.shape[3]))
+        self.r = pr.shape[3] - 1
+        self._dims = {'n_samples': 0, 'n_user_groups': self.user_groups,
+                      'n_item_groups': self.item_groups, 'n_ratings': pr.shape[3]}
+        self._engine = Engine.for_prediction(self.p + 1, self.m + 1, pr.shape[3],
+                                             self.user_groups, self.item_groups)
+        return self
+
     # ------------------------------------------------------------------------ stats
     def choose_best_run(self, rats):
         """Index of the run with the highest accuracy (first on ties)."""

@@ -147,7 +147,7 @@ def test_fixture_one_and_ten_iterations(golden_dir):
 
 
 @pytest.mark.parametrize("K,L,R,S", [(10, 10, 5, 3), (20, 20, 5, 2), (7, 5, 4, 1), (3, 32, 6, 2), (33, 9, 5, 1),
-                                     (1, 1, 2, 1), (64, 48, 5, 1), (130, 70, 3, 1), (12, 28, 10, 2)])
+                                     (1, 1, 2, 1), (64, 48, 5, 1), (130, 70, 3, 1), (12, 28, 10, 2), (20, 20, 5, 5)])
 @pytest.mark.parametrize("heavy", [False, True])
 def test_batched_runs_one_iteration_vs_oracle(K, L, R, S, heavy):
     from mmsbm_b200.engine import Engine
@@ -365,6 +365,34 @@ def test_mmsbm_fixture_known_answers(golden_dir, tmp_path, monkeypatch):
     assert list(sc["objects"]["theta"].index) == meta["theta_index"]
     assert rel_err(mm.results[0]["theta"], g["theta10"]) < 1e-9
     assert mm.score(silent=False)["stats"]["accuracy"] == st["accuracy"]     # logging branch
+
+
+def test_save_load_round_trip(tmp_path, monkeypatch):
+    """MMSBM.save / MMSBM.load: the restored model predicts and scores bit-identically, keeps the
+    dictionaries and every run, and refuses what needs the training rows."""
+    monkeypatch.chdir(tmp_path)
+    from mmsbm_b200 import MMSBM
+    mm = MMSBM(3, 2, iterations=12, sampling=3, seed=5)
+    mm.fit(mock_data(1))
+    pred = mm.predict(mock_data(2))
+    sc = mm.score(silent=True)
+    path = str(tmp_path / "model.npz")
+    mm.save(path)
+    back = MMSBM.load(path)
+    assert back.sampling == 3 and back.user_groups == 3 and back.iterations == 12
+    assert back.data_handler.return_dicts() == mm.data_handler.return_dicts()
+    for a, b in zip(mm.results, back.results):
+        for k in ("theta", "eta", "pr"):
+            np.testing.assert_array_equal(a[k], b[k])
+        assert a["likelihood"] == b["likelihood"]
+    np.testing.assert_array_equal(back.predict(mock_data(2)), pred)
+    sc2 = back.score(silent=True)
+    assert sc2["stats"] == sc["stats"]
+    assert sc2["objects"]["theta"].equals(sc["objects"]["theta"])
+    with pytest.raises(RuntimeError):
+        back._engine.run(1)
+    with pytest.raises(AssertionError):
+        MMSBM(2, 2).save(path)                       # not fitted
 
 
 def test_mmsbm_best_run_choice(golden_dir, tmp_path, monkeypatch):

@@ -164,3 +164,23 @@ def test_empty_rating_level_keeps_zero_slab():
     assert np.all(npr[:, :, 1] == 0) and np.all(npr[:, :, 0] > 0)
     z = orc.normalize_pr(np.zeros((2, 2, 3)))
     assert np.all(z == 0)
+
+
+def test_numba_port_against_reference_numba_kernel_and_numpy_oracle(golden_dir):
+    """oracle/mmsbm_oracle_numba.py (the CPU baseline bench.py times next to the numpy port):
+    omega against the output of the reference's numba kernel on its own toy, the M-step sums and
+    a full iteration against the numpy oracle (fastmath and eps-added-not-clamped: ~1e-12)."""
+    onb = pytest.importorskip("oracle.mmsbm_oracle_numba")
+    g = _load(golden_dir, "toy_backends.npz")
+    for tag in ("omega", "prod"):
+        args = [g[f"{tag}_{k}"] for k in ("data", "theta", "eta", "pr")]
+        np.testing.assert_allclose(onb.omegas(*args), g[f"{tag}_omegas_numba"], rtol=1e-14)
+        for got, want in zip(onb.em_sums(*args), (g[f"{tag}_ntheta"], g[f"{tag}_neta"], g[f"{tag}_npr"])):
+            np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-300)
+    m = _load(golden_dir, "medium.npz")
+    fu, fi = orc.degree_factors(m["data"], m["theta"].shape[1], m["eta"].shape[1])
+    want = orc.em_iteration(m["data"], m["theta"], m["eta"], m["pr"], fu, fi)
+    for chunk in (None, 1000):
+        got = onb.em_iteration(m["data"], m["theta"], m["eta"], m["pr"], fu, fi, chunk=chunk)
+        for a, b in zip(got, want):
+            np.testing.assert_allclose(a, b, rtol=1e-11, atol=1e-300)
