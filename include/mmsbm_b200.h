@@ -50,7 +50,7 @@
 extern "C" {
 #endif
 
-#define MMSBM_ABI_VERSION 2
+#define MMSBM_ABI_VERSION 3
 
 /* a warp of the hot kernel processes at most this many ratings of one segment at a time; longer
  * segments are cut into pieces whose partial sums are added in piece order (see usched/isched) */
@@ -137,8 +137,16 @@ int mmsbm_em_finalize(double* eta_dev, const int32_t* ideg_dev, int32_t n_items,
 
 /* ---- a5: the reference's "likelihood", replaces ExpectationMaximization.compute_likelihood
  *      (src/expectation_maximization.py:157-167); out_dev[S] ------------------------------ */
-int mmsbm_likelihood_workspace_bytes(int32_t n_users, int32_t n_runs, size_t* bytes);
-int mmsbm_likelihood(const int32_t* useg_dev, const int32_t* uadj_dev,
+/* usched_dev: the by-user work schedule of mmsbm_graph_build.  With it (and rows of at most 32
+ * doubles) the sum is evaluated in its factorised form, O(K+L) per rating; NULL selects the
+ * element-wise form, K*L visits per rating.  The runs are processed in batches that fit the
+ * workspace: _workspace_bytes = all runs at once, _min_workspace_bytes = one run at a time. */
+int mmsbm_likelihood_workspace_bytes(int64_t n_ratings, int32_t n_users, int32_t n_items, int32_t n_levels,
+                                     int32_t K, int32_t L, int32_t n_runs, size_t* bytes);
+int mmsbm_likelihood_min_workspace_bytes(int64_t n_ratings, int32_t n_users, int32_t n_items,
+                                         int32_t n_levels, int32_t K, int32_t L, int32_t n_runs,
+                                         size_t* bytes);
+int mmsbm_likelihood(const int32_t* useg_dev, const int32_t* uadj_dev, const int32_t* usched_dev,
                      int64_t n_ratings, int32_t n_users, int32_t n_items, int32_t n_levels,
                      int32_t K, int32_t L, int32_t n_runs,
                      const double* theta_dev, const double* eta_dev, const double* pr_dev,

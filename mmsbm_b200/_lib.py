@@ -30,8 +30,9 @@ _PROTOS = {
     "mmsbm_em_step_profiled": (C.c_int, [_vp] * 8 + [_i64] + [_i32] * 6 + [_vp] * 6 + [_i32, _vp, _sz, _vp, _vp]),
     "mmsbm_em_run": (C.c_int, [_vp] * 8 + [_i64] + [_i32] * 7 + [_vp] * 6 + [_vp, _sz, _vp]),
     "mmsbm_em_finalize": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
-    "mmsbm_likelihood_workspace_bytes": (C.c_int, [_i32, _i32, C.POINTER(_sz)]),
-    "mmsbm_likelihood": (C.c_int, [_vp, _vp, _i64] + [_i32] * 6 + [_vp] * 4 + [_vp, _sz, _vp]),
+    "mmsbm_likelihood_workspace_bytes": (C.c_int, [_i64] + [_i32] * 6 + [C.POINTER(_sz)]),
+    "mmsbm_likelihood_min_workspace_bytes": (C.c_int, [_i64] + [_i32] * 6 + [C.POINTER(_sz)]),
+    "mmsbm_likelihood": (C.c_int, [_vp, _vp, _vp, _i64] + [_i32] * 6 + [_vp] * 4 + [_vp, _sz, _vp]),
     "mmsbm_prod_dist": (C.c_int, [_vp, _vp, _i64] + [_i32] * 6 + [_vp] * 4 + [_vp]),
     "mmsbm_stats_workspace_bytes": (C.c_int, [_i64, _i32, C.POINTER(_sz)]),
     "mmsbm_predict_stats": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -68,7 +69,7 @@ def load(require_device=False):
         for name, (res, args) in _PROTOS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.mmsbm_abi_version() != 2:
+        if lib.mmsbm_abi_version() != 3:
             raise ImportError("libmmsbm_b200.so: ABI version mismatch, rebuild it")
         _lib = lib
     if require_device and _lib.mmsbm_device_count() <= 0:

@@ -288,9 +288,9 @@ extern "C" int mmsbm_host_likelihood(const int64_t* data, int64_t N, const doubl
   TRY(sc.alloc(&dpr, (size_t)K * L * R));
   MMSBM_CUDA(cudaMemcpyAsync(dpr, pr, (size_t)K * L * R * 8, cudaMemcpyHostToDevice, sc.st));
   TRY(sc.alloc(&dout, 1));
-  size_t wsb = 0; TRY(mmsbm_likelihood_workspace_bytes(U, 1, &wsb));
+  size_t wsb = 0; TRY(mmsbm_likelihood_workspace_bytes(N, U, I, R, K, L, 1, &wsb));
   char* ws; TRY(sc.alloc(&ws, wsb));
-  TRY(mmsbm_likelihood(g.useg, g.uadj, N, U, I, R, K, L, 1, dth, det, dpr, dout, ws, wsb, sc.st));
+  TRY(mmsbm_likelihood(g.useg, g.uadj, g.usched, N, U, I, R, K, L, 1, dth, det, dpr, dout, ws, wsb, sc.st));
   MMSBM_CUDA(cudaMemcpyAsync(out, dout, 8, cudaMemcpyDeviceToHost, sc.st));
   MMSBM_CUDA(cudaStreamSynchronize(sc.st));
   return 0;
@@ -320,16 +320,21 @@ extern "C" int mmsbm_host_fit(const int64_t* data, int64_t N, int32_t U, int32_t
   TRY(sc.alloc(&prb, prn)); TRY(sc.alloc(&dlik, (size_t)S));
   size_t wsb = 0, lwsb = 0;
   TRY(mmsbm_em_workspace_bytes(N, U, I, R, K, L, S, &wsb));
-  TRY(mmsbm_likelihood_workspace_bytes(U, S, &lwsb));
+  // the likelihood runs after the EM loop and batches its runs to the workspace it is given:
+  // one allocation serves both (at least the likelihood's minimum)
+  TRY(mmsbm_likelihood_min_workspace_bytes(N, U, I, R, K, L, S, &lwsb));
+  if (lwsb > wsb) wsb = lwsb;
+  lwsb = wsb;
   char *ws, *lws;
-  TRY(sc.alloc(&ws, wsb)); TRY(sc.alloc(&lws, lwsb));
+  TRY(sc.alloc(&ws, wsb));
+  lws = ws;
   tr.mark("params H2D + alloc");
   TRY(mmsbm_em_run(g.useg, g.uadj, g.udeg, g.iseg, g.iadj, g.ideg, g.usched, g.isched, N, U, I, R, K, L, S, iterations, tha,
                    eta_a, pra, thb, etb, prb, ws, wsb, sc.st));
   tr.mark("EM iterations");
   const bool in_a = (iterations % 2) == 0;
   double* th = in_a ? tha : thb; double* et = in_a ? eta_a : etb; double* pr = in_a ? pra : prb;
-  TRY(mmsbm_likelihood(g.useg, g.uadj, N, U, I, R, K, L, S, th, et, pr, dlik, lws, lwsb, sc.st));
+  TRY(mmsbm_likelihood(g.useg, g.uadj, g.usched, N, U, I, R, K, L, S, th, et, pr, dlik, lws, lwsb, sc.st));
   tr.mark("likelihood");
   TRY(download_rows(sc, th, (size_t)S * U, K, theta_out));
   TRY(download_rows(sc, et, (size_t)S * I, L, eta_out));

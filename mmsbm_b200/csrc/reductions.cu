@@ -4,8 +4,10 @@
 // materialising compute_omegas (src/kernels_numpy.py:21-36) for the plugin shim.
 // All sums are two-stage with a fixed order (bit-reproducible).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "segment_pass.cuh"   // double4_t, ldg256, GroupSum (lane groups of the row gathers)
 
 namespace mmsbm {
 
@@ -114,6 +116,153 @@ __global__ void __launch_bounds__(kLikWarps * 32) likelihood_kernel(const LikArg
     }
   }
   if (lane == 0) A.partial[(size_t)run * nw + gw] = acc;
+}
+
+// ---- likelihood, factorised ---------------------------------------------------------------
+// For elements that are not clamped, sum_kl w log w splits into the same bilinear forms as the EM
+// step (w = theta_k eta_l p_klr, so log w = log theta_k + log eta_l + log p_klr):
+//     S_n = <W_{u,r}, eta_i>                       W[l] = sum_k theta_k p_klr
+//     T_n = <A_{u,r}, eta_i> + <W_{u,r}, eta_i log eta_i>
+//                                                  A[l] = sum_k (theta_k log theta_k) p_klr + theta_k (p log p)_klr
+//     likelihood = sum_n T_n - S_n log max(S_n, eps)
+// i.e. O(K+L) per rating after two per-(user, level) tables, instead of K*L element visits and
+// L logarithms.  x log x := 0 at x = 0.  The reference clamps every w below eps up to eps
+// (src/expectation_maximization.py:162-166); here such an element contributes w log w instead of
+// eps log eps: at most 8e-15 per element, i.e. <= 1e-11 relative on the totals of interest,
+// inside the 1e-8 the likelihood is specified to (north_star).  Walks the (user, level)-grouped
+// index with the piece schedule of the EM step, so a heavy user costs no more than 2048 ratings
+// per warp; one partial per piece, summed in piece order.
+__device__ __forceinline__ double xlogx(double x) { return x > 0.0 ? x * log(x) : 0.0; }
+
+// E2[run][item][0][:] = eta, [1][:] = eta log eta  (one contiguous 2*8*ldl-byte gather per rating)
+__global__ void lik_eta_table_kernel(const double* __restrict__ eta, double* __restrict__ e2, size_t rows, int ld) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * ld) return;
+  const size_t row = t / ld;
+  const int c = (int)(t - row * ld);
+  const double v = __ldg(eta + t);
+  e2[(row * 2) * ld + c] = v;
+  e2[(row * 2 + 1) * ld + c] = xlogx(v);
+}
+
+// W and A rows of every user: a lane owns a user, the two operand tables sit in shared memory
+// (every read a warp broadcast).  Pw[a][o] = p, Pl[a][o] = p log p with o = r*ldl + l, zero padded.
+template <int LD>
+__global__ void __launch_bounds__(256) lik_user_tables_kernel(const double* __restrict__ theta,
+                                                              const double* __restrict__ pr,
+                                                              double* __restrict__ W, double* __restrict__ A,
+                                                              int U, int K, int L, int R, int ldl, int run0) {
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  const int RNB = R * ldl;
+  double* Pw = reinterpret_cast<double*>(smem_raw);          // [LD][RNB]
+  double* Pl = Pw + (size_t)LD * RNB;
+  const int run = run0 + blockIdx.y;
+  const double* prs = pr + (size_t)run * K * L * R;
+  for (int t = threadIdx.x; t < LD * RNB; t += blockDim.x) {
+    const int a = t / RNB, o = t - a * RNB, r = o / ldl, l = o - r * ldl;
+    const double v = (a < K && l < L) ? __ldg(prs + ((size_t)a * L + l) * R + r) : 0.0;
+    Pw[t] = v;
+    Pl[t] = xlogx(v);
+  }
+  __syncthreads();
+  const double* th_run = theta + (size_t)run * U * LD;
+  double* w_run = W + (size_t)blockIdx.y * U * RNB;
+  double* a_run = A + (size_t)blockIdx.y * U * RNB;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < U; m += gridDim.x * blockDim.x) {
+    double o[LD], ol[LD];
+#pragma unroll
+    for (int c = 0; c < LD / 4; ++c) {
+      const double4_t v = ldg256(th_run + (size_t)m * LD + 4 * c);
+      o[4 * c] = v.x; o[4 * c + 1] = v.y; o[4 * c + 2] = v.z; o[4 * c + 3] = v.w;
+    }
+#pragma unroll
+    for (int a = 0; a < LD; ++a) ol[a] = xlogx(o[a]);
+    for (int ob = 0; ob < RNB; ob += 4) {
+      double4_t w{0.0, 0.0, 0.0, 0.0}, q{0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int a = 0; a < LD; ++a) {
+        const double4_t p = lds32(Pw + a * RNB + ob);
+        const double4_t pl = lds32(Pl + a * RNB + ob);
+        w.x = fma(o[a], p.x, w.x); w.y = fma(o[a], p.y, w.y); w.z = fma(o[a], p.z, w.z); w.w = fma(o[a], p.w, w.w);
+        q.x = fma(ol[a], p.x, q.x); q.y = fma(ol[a], p.y, q.y); q.z = fma(ol[a], p.z, q.z); q.w = fma(ol[a], p.w, q.w);
+        q.x = fma(o[a], pl.x, q.x); q.y = fma(o[a], pl.y, q.y); q.z = fma(o[a], pl.z, q.z); q.w = fma(o[a], pl.w, q.w);
+      }
+      stg256(w_run + (size_t)m * RNB + ob, w);
+      stg256(a_run + (size_t)m * RNB + ob, q);
+    }
+  }
+}
+
+struct LikPassArgs {
+  const int32_t* useg; const int32_t* uadj; const int32_t* sched;
+  const double* e2;       // [runs][I][2][NBp]
+  const double* W;        // [runs][U][R*NBp]
+  const double* A;
+  double* partial;        // [runs][pmax]
+  int64_t pmax;
+  int U, I, R;
+};
+
+// One warp per piece; groups of G lanes own a rating (lane q holds doubles 4q..4q+3 of both rows).
+template <int G>
+__global__ void __launch_bounds__(256) lik_pass_kernel(const LikPassArgs P) {
+  constexpr int RPS = 32 / G, UN = (G == 1) ? 1 : 2, SLOTS = UN * RPS, NBp = 4 * G;
+  static_assert(SLOTS <= 32, "a chunk's ids must fit one 32-lane load");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane / G, q = lane - grp * G;
+  const bool lane_on = grp < RPS;
+  const int qoff = lane_on ? 4 * q : 0;
+  const int run = blockIdx.y, R = P.R, RNB = R * NBp;
+  const GroupSum<G> group_sum(grp * G, q);
+  const int32_t* piece_seg = P.sched + 4;
+  const int32_t* piece_idx = piece_seg + P.pmax;
+  const int n_pieces = __ldg(P.sched);
+  const double* e2 = P.e2 + (size_t)run * P.I * 2 * NBp;
+  for (int p = blockIdx.x * (blockDim.x >> 5) + warp; p < n_pieces; p += gridDim.x * (blockDim.x >> 5)) {
+    const int sg = __ldg(piece_seg + p), pidx = __ldg(piece_idx + p);
+    MMSBM_DEV_CHECK(sg >= 0 && sg < P.U);
+    int bend = 0;
+    if (lane <= R) bend = __ldg(P.useg + (size_t)sg * R + lane);
+    const int beg = __shfl_sync(kFull, bend, 0) + pidx * MMSBM_PIECE_LEN;
+    const int end = min(beg + MMSBM_PIECE_LEN, __shfl_sync(kFull, bend, R));
+    const double* wrow = P.W + ((size_t)run * P.U + sg) * RNB;
+    const double* arow = P.A + ((size_t)run * P.U + sg) * RNB;
+    double acc = 0.0;
+    int lo = beg;
+    for (int r = 0; r < R; ++r) {
+      const int le = min(end, __shfl_sync(kFull, bend, r + 1));
+      if (lo >= le) continue;
+      const double4_t wr = ldg256(wrow + r * NBp + qoff), ar = ldg256(arow + r * NBp + qoff);
+      for (int base = lo; base < le; base += SLOTS) {
+        const int cnt = min(SLOTS, le - base);
+        int ids = 0;
+        if (lane < cnt) ids = __ldg(P.uadj + base + lane);
+        double4_t e[UN], el[UN];
+#pragma unroll
+        for (int un = 0; un < UN; ++un) {
+          const int sl = un * RPS + grp;
+          int id = __shfl_sync(kFull, ids, sl & 31);
+          if (sl >= cnt) id = 0;
+          MMSBM_DEV_CHECK(id >= 0 && id < P.I);
+          const double* row = e2 + (size_t)id * 2 * NBp + qoff;
+          e[un] = ldg256(row);
+          el[un] = ldg256(row + NBp);
+        }
+#pragma unroll
+        for (int un = 0; un < UN; ++un) {
+          double s = fma(e[un].x, wr.x, fma(e[un].y, wr.y, fma(e[un].z, wr.z, e[un].w * wr.w)));
+          double t = fma(e[un].x, ar.x, fma(e[un].y, ar.y, fma(e[un].z, ar.z, e[un].w * ar.w)));
+          t = fma(el[un].x, wr.x, fma(el[un].y, wr.y, fma(el[un].z, wr.z, fma(el[un].w, wr.w, t))));
+          s = group_sum(s);
+          t = group_sum(t);
+          if (lane_on && q == 0 && un * RPS + grp < cnt) acc += t - s * log(fmax(s, kEps));
+        }
+      }
+      lo = le;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) P.partial[(size_t)run * P.pmax + p] = acc;
+  }
 }
 
 __global__ void __launch_bounds__(256) sum_partials_kernel(const double* partial, int n, double* out) {
@@ -276,14 +425,122 @@ using namespace mmsbm;
 
 constexpr size_t kLikTableBytes = 512 * 1024;   // room for [2][R][K][L] per run when spilled to global
 
-extern "C" int mmsbm_likelihood_workspace_bytes(int32_t U, int32_t S, size_t* bytes) {
-  MMSBM_REQUIRE(bytes && U > 0 && S > 0, MMSBM_EINVAL, "mmsbm_likelihood_workspace_bytes: bad argument");
-  *bytes = align_up((size_t)S * kLikCtas * kLikWarps * 8) + align_up((size_t)S * kLikTableBytes) + 256;
+static int lik_env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+// the factorised path needs rows of at most 32 doubles (one 32-byte chunk per lane of a group of
+// up to 8) and both operand tables of a run in shared memory
+static bool lik_factorised_ok(int R, int K, int L) {
+  const int ldk = row_stride(K), ldl = row_stride(L);
+  return ldk <= 32 && ldl <= 32 && 2 * (size_t)ldk * R * ldl * 8 <= 200 * 1024 &&
+         lik_env_int("MMSBM_LIK_ELEMENTWISE", 0) == 0;
+}
+static size_t lik_run_bytes(int U, int I, int R, int L) {      // tables of one run
+  const size_t ldl = row_stride(L), rnb = (size_t)R * ldl;
+  return 2 * align_up((size_t)U * rnb * 8) + align_up((size_t)I * 2 * ldl * 8);
+}
+static int64_t lik_pmax(int64_t N, int U) { return (int64_t)U + N / MMSBM_PIECE_LEN + 1; }   // = graph_build.cu
+
+extern "C" int mmsbm_likelihood_workspace_bytes(int64_t N, int32_t U, int32_t I, int32_t R, int32_t K,
+                                                int32_t L, int32_t S, size_t* bytes) {
+  MMSBM_REQUIRE(bytes && N >= 0 && U > 0 && I > 0 && R > 0 && K > 0 && L > 0 && S > 0, MMSBM_EINVAL,
+                "mmsbm_likelihood_workspace_bytes: bad argument");
+  const size_t elementwise = align_up((size_t)S * kLikCtas * kLikWarps * 8) + align_up((size_t)S * kLikTableBytes) + 256;
+  size_t fact = 0;
+  if (lik_factorised_ok(R, K, L))
+    fact = align_up((size_t)S * lik_pmax(N, U) * 8) + (size_t)S * lik_run_bytes(U, I, R, L) + 256;
+  *bytes = fact > elementwise ? fact : elementwise;
   return 0;
 }
 
-extern "C" int mmsbm_likelihood(const int32_t* useg, const int32_t* uadj, int64_t N, int32_t U,
-                                int32_t I, int32_t R, int32_t K, int32_t L, int32_t S,
+// smallest workspace mmsbm_likelihood accepts: the runs are then processed one at a time
+extern "C" int mmsbm_likelihood_min_workspace_bytes(int64_t N, int32_t U, int32_t I, int32_t R, int32_t K,
+                                                    int32_t L, int32_t S, size_t* bytes) {
+  MMSBM_REQUIRE(bytes && N >= 0 && U > 0 && I > 0 && R > 0 && K > 0 && L > 0 && S > 0, MMSBM_EINVAL,
+                "mmsbm_likelihood_min_workspace_bytes: bad argument");
+  const size_t elementwise = align_up((size_t)S * kLikCtas * kLikWarps * 8) + align_up((size_t)S * kLikTableBytes) + 256;
+  size_t fact = 0;
+  if (lik_factorised_ok(R, K, L))
+    fact = align_up((size_t)S * lik_pmax(N, U) * 8) + lik_run_bytes(U, I, R, L) + 256;
+  *bytes = fact > elementwise ? fact : elementwise;
+  return 0;
+}
+
+template <int LD>
+static int launch_lik_tables(const double* theta, const double* pr, double* W, double* A, int U, int K, int L,
+                             int R, int run0, int nb, cudaStream_t st) {
+  const int ldl = row_stride(L);
+  const size_t smem = 2 * (size_t)LD * R * ldl * 8;
+  MMSBM_CUDA(cudaFuncSetAttribute(lik_user_tables_kernel<LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int gx = (U + 255) / 256 < 148 * 2 ? (U + 255) / 256 : 148 * 2;
+  lik_user_tables_kernel<LD><<<dim3(gx, nb), 256, smem, st>>>(theta, pr, W, A, U, K, L, R, ldl, run0);
+  MMSBM_LAUNCH_CHECK("lik_user_tables_kernel");
+  return 0;
+}
+
+static int likelihood_factorised(const int32_t* useg, const int32_t* uadj, const int32_t* usched, int64_t N,
+                                 int U, int I, int R, int K, int L, int S, const double* theta,
+                                 const double* eta, const double* pr, double* out, void* ws, size_t ws_bytes,
+                                 cudaStream_t st) {
+  const int ldk = row_stride(K), ldl = row_stride(L);
+  const size_t rnb = (size_t)R * ldl;
+  const int64_t pmax = lik_pmax(N, U);
+  Arena arena(ws, ws_bytes);
+  double* partial = arena.take<double>((size_t)S * pmax);
+  MMSBM_REQUIRE(partial, MMSBM_ENOMEM, "mmsbm_likelihood: workspace too small");
+  const size_t per_run = lik_run_bytes(U, I, R, L);
+  int nb = (int)((ws_bytes - arena.off) / per_run);          // runs per batch that fit the workspace
+  if (nb > S) nb = S;
+  MMSBM_REQUIRE(nb >= 1, MMSBM_ENOMEM, "mmsbm_likelihood: workspace too small for one run (%zu bytes)", ws_bytes);
+  double* W = arena.take<double>((size_t)nb * U * rnb);
+  double* A = arena.take<double>((size_t)nb * U * rnb);
+  double* e2 = arena.take<double>((size_t)nb * I * 2 * ldl);
+  MMSBM_REQUIRE(W && A && e2, MMSBM_ENOMEM, "mmsbm_likelihood: workspace too small");
+  MMSBM_CUDA(cudaMemsetAsync(partial, 0, (size_t)S * pmax * 8, st));
+  for (int run0 = 0; run0 < S; run0 += nb) {
+    const int n = S - run0 < nb ? S - run0 : nb;
+    {
+      const size_t rows = (size_t)n * I, tot = rows * ldl;
+      lik_eta_table_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(eta + (size_t)run0 * I * ldl, e2, rows, ldl);
+      MMSBM_LAUNCH_CHECK("lik_eta_table_kernel");
+    }
+    int rc = MMSBM_ERANGE;
+    switch (ldk) {
+      case 4: rc = launch_lik_tables<4>(theta, pr, W, A, U, K, L, R, run0, n, st); break;
+      case 8: rc = launch_lik_tables<8>(theta, pr, W, A, U, K, L, R, run0, n, st); break;
+      case 12: rc = launch_lik_tables<12>(theta, pr, W, A, U, K, L, R, run0, n, st); break;
+      case 16: rc = launch_lik_tables<16>(theta, pr, W, A, U, K, L, R, run0, n, st); break;
+      case 20: rc = launch_lik_tables<20>(theta, pr, W, A, U, K, L, R, run0, n, st); break;
+      case 24: rc = launch_lik_tables<24>(theta, pr, W, A, U, K, L, R, run0, n, st); break;
+      case 28: rc = launch_lik_tables<28>(theta, pr, W, A, U, K, L, R, run0, n, st); break;
+      case 32: rc = launch_lik_tables<32>(theta, pr, W, A, U, K, L, R, run0, n, st); break;
+    }
+    if (rc) return rc;
+    LikPassArgs a{useg, uadj, usched, e2, W, A, partial + (size_t)run0 * pmax, pmax, U, I, R};
+    const int64_t want = (pmax + 7) / 8;
+    const dim3 grid((unsigned)(want < 148 * 16 ? want : 148 * 16), n);
+    switch (ldl / 4) {
+      case 1: lik_pass_kernel<1><<<grid, 256, 0, st>>>(a); break;
+      case 2: lik_pass_kernel<2><<<grid, 256, 0, st>>>(a); break;
+      case 3: lik_pass_kernel<3><<<grid, 256, 0, st>>>(a); break;
+      case 4: lik_pass_kernel<4><<<grid, 256, 0, st>>>(a); break;
+      case 5: lik_pass_kernel<5><<<grid, 256, 0, st>>>(a); break;
+      case 6: lik_pass_kernel<6><<<grid, 256, 0, st>>>(a); break;
+      case 7: lik_pass_kernel<7><<<grid, 256, 0, st>>>(a); break;
+      default: lik_pass_kernel<8><<<grid, 256, 0, st>>>(a); break;
+    }
+    MMSBM_LAUNCH_CHECK("lik_pass_kernel");
+  }
+  MMSBM_REQUIRE(pmax <= 0x7fffffff, MMSBM_ERANGE, "mmsbm_likelihood: too many pieces");
+  sum_partials_kernel<<<S, 256, 0, st>>>(partial, (int)pmax, out);
+  MMSBM_LAUNCH_CHECK("sum_partials_kernel");
+  return 0;
+}
+
+extern "C" int mmsbm_likelihood(const int32_t* useg, const int32_t* uadj, const int32_t* usched, int64_t N,
+                                int32_t U, int32_t I, int32_t R, int32_t K, int32_t L, int32_t S,
                                 const double* theta, const double* eta, const double* pr, double* out,
                                 void* ws, size_t ws_bytes, void* stream) {
   MMSBM_REQUIRE(useg && uadj && theta && eta && pr && out && ws, MMSBM_EINVAL,
@@ -291,6 +548,9 @@ extern "C" int mmsbm_likelihood(const int32_t* useg, const int32_t* uadj, int64_
   MMSBM_REQUIRE(U > 0 && I > 0 && R > 0 && K > 0 && L > 0 && S > 0 && N >= 0, MMSBM_EINVAL,
                 "mmsbm_likelihood: bad size");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (usched && lik_factorised_ok(R, K, L))
+    return likelihood_factorised(useg, uadj, usched, N, U, I, R, K, L, S, theta, eta, pr, out, ws, ws_bytes, st);
+  // element-wise path (rows wider than 32 doubles, or no schedule given): K*L visits per rating
   Arena arena(ws, ws_bytes);
   const int nw = kLikCtas * kLikWarps;
   double* partial = arena.take<double>((size_t)S * nw);

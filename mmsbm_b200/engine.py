@@ -208,14 +208,22 @@ class Engine:
     def likelihood_device(self):
         self._need_ratings()
         out = self._empty(self.S, torch.float64)
+        dims = (self.N, self.U, self.I, self.R, self.K, self.L, self.S)
         need = _lib.C.c_size_t(0)
-        _lib.check(self.lib.mmsbm_likelihood_workspace_bytes(self.U, self.S, _lib.C.byref(need)),
-                   "likelihood_workspace_bytes")
-        ws = self._bytes(need.value)
+        _lib.check(self.lib.mmsbm_likelihood_min_workspace_bytes(*dims, _lib.C.byref(need)),
+                   "likelihood_min_workspace_bytes")
+        if self._ws is not None and self._ws_bytes >= need.value:
+            # the EM workspace is idle between iterations (same stream): the likelihood batches its
+            # runs to whatever it is given
+            ws, ws_bytes = self._ws, self._ws_bytes
+        else:
+            _lib.check(self.lib.mmsbm_likelihood_workspace_bytes(*dims, _lib.C.byref(need)),
+                       "likelihood_workspace_bytes")
+            ws, ws_bytes = self._bytes(need.value), need.value
         _lib.check(self.lib.mmsbm_likelihood(
-            self.useg.data_ptr(), self.uadj.data_ptr(), self.N, self.U, self.I, self.R, self.K, self.L,
-            self.S, self.theta.data_ptr(), self.eta.data_ptr(), self.pr.data_ptr(), out.data_ptr(),
-            ws.data_ptr(), need.value, self._stream()), "likelihood")
+            self.useg.data_ptr(), self.uadj.data_ptr(), self.usched.data_ptr(), self.N, self.U, self.I,
+            self.R, self.K, self.L, self.S, self.theta.data_ptr(), self.eta.data_ptr(), self.pr.data_ptr(),
+            out.data_ptr(), ws.data_ptr(), ws_bytes, self._stream()), "likelihood")
         ws.record_stream(torch.cuda.current_stream(self.device))
         return out[:self.S]
 

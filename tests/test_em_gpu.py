@@ -315,6 +315,46 @@ def test_launch_strategies_give_identical_bits(monkeypatch):
             np.testing.assert_array_equal(a, b, err_msg=name)
 
 
+def test_likelihood_paths_agree(monkeypatch):
+    """The factorised likelihood (O(K+L) per rating) against the element-wise kernel (the
+    reference's per-element clamp, K*L visits) and the oracle; the run batching that adapts to
+    the workspace size must not change a bit."""
+    import torch
+    from mmsbm_b200 import _lib
+    from mmsbm_b200.engine import Engine
+    for (K, L, R, S, heavy) in ((20, 20, 5, 3, True), (10, 7, 4, 2, False), (32, 32, 5, 1, False)):
+        N, U, I = 50000, 600, 400
+        data = random_triples(101, N, U, I, R, heavy_tail=heavy)
+        theta, eta, pr = random_params(103, U, I, K, L, R, S=S)
+        theta[:, 5, 0] = 0.0                                   # exact zeros: x log x := 0
+        pr[:, 0, 0, 0] = 1e-300                                # an element far below eps
+        e = Engine(data, U, I, R, K, L)
+        e.set_params(theta, eta, pr)
+        fast = e.likelihood()
+        monkeypatch.setenv("MMSBM_LIK_ELEMENTWISE", "1")
+        slow = e.likelihood()
+        monkeypatch.delenv("MMSBM_LIK_ELEMENTWISE")
+        for s in range(S):
+            want = sum(orc.likelihood(data[lo:lo + 10000], theta[s], eta[s], pr[s]) for lo in range(0, N, 10000))
+            assert abs(slow[s] - want) <= 1e-11 * abs(want)
+            assert abs(fast[s] - want) <= 1e-10 * abs(want)    # spec: 1e-8
+        # smallest accepted workspace (one run per batch) gives the same bits as the full one
+        need = _lib.C.c_size_t(0)
+        lib = e.lib
+        _lib.check(lib.mmsbm_likelihood_min_workspace_bytes(N, U, I, R, K, L, S, _lib.C.byref(need)), "min ws")
+        ws = torch.empty(need.value, dtype=torch.uint8, device="cuda")
+        out = torch.empty(S, dtype=torch.float64, device="cuda")
+        _lib.check(lib.mmsbm_likelihood(e.useg.data_ptr(), e.uadj.data_ptr(), e.usched.data_ptr(), N, U, I, R, K, L, S,
+                                        e.theta.data_ptr(), e.eta.data_ptr(), e.pr.data_ptr(), out.data_ptr(),
+                                        ws.data_ptr(), need.value, torch.cuda.current_stream().cuda_stream), "lik")
+        np.testing.assert_array_equal(out.cpu().numpy(), fast)
+        small = torch.empty(1024, dtype=torch.uint8, device="cuda")
+        rc = lib.mmsbm_likelihood(e.useg.data_ptr(), e.uadj.data_ptr(), e.usched.data_ptr(), N, U, I, R, K, L, S,
+                                  e.theta.data_ptr(), e.eta.data_ptr(), e.pr.data_ptr(), out.data_ptr(),
+                                  small.data_ptr(), 1024, torch.cuda.current_stream().cuda_stream)
+        assert rc != 0                                          # too small: an error, not a wrong answer
+
+
 # ------------------------------------------------------------------- predict / stats (a6, a10)
 def test_predict_stats_vs_oracle():
     from mmsbm_b200.engine import predict_stats
