@@ -87,12 +87,44 @@ inline size_t seg_smem_bytes(const SegArgs& a, int runs) {
 template <int G>
 struct GroupSum {
   int s1, s2, s4, s6;
+  int lead, r1, r2, r3;          // G == 5: sources of the three reduce-scatter stages of sum3()
+  bool is0, is1, is2, is3, is14, is03;
   __device__ __forceinline__ GroupSum(int leader, int q) {
     s1 = (leader + (q + 1) % G) & 31;
     s2 = (leader + (q + 2) % G) & 31;
     s4 = (leader + (q + 4) % G) & 31;
     s6 = (leader + (q + 6) % G) & 31;
+    lead = leader & 31;
+    is0 = q == 0; is1 = q == 1; is2 = q == 2; is3 = q == 3; is14 = (q == 1) | (q == 4); is03 = (q == 0) | (q == 3);
+    // stage 1: 0<-1 1<-2 2<-0 3<-4 4<-3   stage 2: 0<-2 1<-4 2<-3 4<-0   stage 3: 0<-3 1<-4 2<-1
+    r1 = (leader + (q == 0 ? 1 : q == 1 ? 2 : q == 2 ? 0 : q == 3 ? 4 : 3)) & 31;
+    r2 = (leader + (q == 0 ? 2 : q == 1 ? 4 : q == 2 ? 3 : q == 3 ? 3 : 0)) & 31;
+    r3 = (leader + (q == 0 ? 3 : q == 1 ? 4 : q == 2 ? 1 : q)) & 31;
   }
+  // G == 5 only.  Sums of THREE values over the 5 lanes of a group by reduce-scatter: 3 shuffle
+  // stages leave the total of a0 on lane 0, of a1 on lane 1, of a2 on lane 2 (12 additions in 3
+  // rounds of <= 5, every lane publishes one value and reads one lane per round) -- against 9
+  // stages for three separate all-reduces.  Returns this lane's total (lanes 3, 4: unused).
+  //   after stage 1   lane0: u=a0{0,1} v=a1{0}   lane1: u=a2{1} v=a1{1,2}   lane2: u=a2{0,2} v=a0{2}
+  //                   lane3: u=a0{3,4} v=a2{3}   lane4: u=a1{3,4} v=a2{4}
+  //   after stage 2   lane0: u=a0{0,1,2}  lane1: u=a2{1,4}  lane2: u=a2{0,2,3}  lane3: u=a0{3,4}
+  //                   lane4: u=a1{0,3,4}
+  //   stage 3         T0 = u0 + u3   T1 = v1 + u4   T2 = u2 + u1
+  __device__ __forceinline__ double sum3(double a0, double a1, double a2) const {
+    static_assert(G == 5, "sum3 is the 5-lane schedule");
+    // lane-constant predicates and plain selects only: no divergent control flow
+    const double pub = is0 ? a2 : (is14 ? a0 : a1);
+    const double tgt = is03 ? a0 : (is2 ? a2 : a1);
+    const double t = tgt + __shfl_sync(kFull, pub, r1);
+    const double vo = is0 ? a1 : (is2 ? a0 : a2);
+    double u = is1 ? a2 : t;
+    const double v = is1 ? t : vo;
+    const double x2 = __shfl_sync(kFull, v, r2);
+    u += is3 ? 0.0 : x2;
+    const double x3 = __shfl_sync(kFull, u, r3);
+    return (is1 ? v : u) + x3;
+  }
+  __device__ __forceinline__ double from_lane(double x, int j) const { return __shfl_sync(kFull, x, lead + j); }
   __device__ __forceinline__ double operator()(double p) const {
     if constexpr (G == 1) {
       return p;
@@ -291,10 +323,21 @@ segment_pass_kernel(const SegArgs A) {
               }
               im[un] = part + part2;
             }
+            if constexpr (G == 5 && NS == 3) {
+              // one reduce-scatter for the three dots, ONE reciprocal per lane, then the three
+              // reciprocals are read back from lanes 0..2 of the group
+              const double mine = rcp_clamped(group_sum.sum3(im[0], im[1], im[2]));
 #pragma unroll
-            for (int un = 0; un < NS; ++un) {
-              im[un] = rcp_clamped(group_sum(im[un]));
-              if (un * RPS + grp >= cnt) im[un] = 0.0;   // idle slot (also the lanes past RPS*GR)
+              for (int un = 0; un < NS; ++un) {
+                im[un] = group_sum.from_lane(mine, un);
+                if (un * RPS + grp >= cnt) im[un] = 0.0;
+              }
+            } else {
+#pragma unroll
+              for (int un = 0; un < NS; ++un) {
+                im[un] = rcp_clamped(group_sum(im[un]));
+                if (un * RPS + grp >= cnt) im[un] = 0.0;   // idle slot (also the lanes past RPS*GR)
+              }
             }
 #pragma unroll
             for (int un = 0; un < NS; ++un) {
