@@ -159,6 +159,61 @@ __global__ void __launch_bounds__(256) k_group256(const double* __restrict__ tab
   out[1 + blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+
+// (F) the em kernel's pair layout through TMA: one cp.async.bulk per rating copies its 320-byte
+// pair row into a per-warp ring of STAGES chunk buffers (SLOTS rows each, completion on an
+// mbarrier per stage); the rows are consumed from shared memory with the kernel's lane mapping
+// (10 lanes x 32 bytes per rating, 3 ratings per step).  Global->register traffic through the
+// L1 LSU data pipe is replaced by TMA writes + LDS reads, and STAGES-1 chunks stay in flight.
+template <int WARPS, int STAGES, int UN>
+__global__ void __launch_bounds__(WARPS * 32) k_tma_pair(const double* __restrict__ table, const int* __restrict__ idx,
+                                                         long n, double* out) {
+  constexpr int RB = 320, RPS = 3, SLOTS = UN * RPS;
+  extern __shared__ __align__(128) unsigned char sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* tile = sm + (size_t)warp * STAGES * SLOTS * RB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + (size_t)WARPS * STAGES * SLOTS * RB) + warp * STAGES;
+  if (lane == 0)
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  const long gw = (long)blockIdx.x * WARPS + warp, nw = (long)gridDim.x * WARPS;
+  const long chunks = n / SLOTS;
+  const int grp = lane / 10, lig = lane % 10;
+  const bool on = grp < RPS;
+  double acc = 0.0;
+  auto issue = [&](long chunk, int st) {
+    if (lane == 0) mbar_expect_tx(&bars[st], SLOTS * RB);
+    __syncwarp();
+    if (lane < SLOTS) {
+      const int id = idx[chunk * SLOTS + lane];
+      bulk_g2s(tile + ((size_t)st * SLOTS + lane) * RB, table + (size_t)id * (RB / 8), RB, &bars[st]);
+    }
+  };
+  long c = gw, cn = gw;
+  int st_issue = 0;
+  for (int s = 0; s < STAGES - 1 && cn < chunks; ++s, cn += nw) { issue(cn, st_issue); st_issue = (st_issue + 1) % STAGES; }
+  int st = 0;
+  uint32_t phase = 0;               // bit s = parity of stage s
+  for (; c < chunks; c += nw) {
+    if (cn < chunks) { issue(cn, st_issue); st_issue = (st_issue + 1) % STAGES; cn += nw; }
+    mbar_wait(&bars[st], (phase >> st) & 1u);
+    phase ^= 1u << st;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      if (on) {
+        const double2* p = reinterpret_cast<const double2*>(tile + ((size_t)st * SLOTS + u * RPS + grp) * RB + lig * 32);
+        const double2 a = p[0], b = p[1];
+        acc = fma(a.x, 1.0000001, acc); acc = fma(a.y, 0.9999999, acc);
+        acc = fma(b.x, 1.0000001, acc); acc = fma(b.y, 0.9999999, acc);
+      }
+    }
+    __syncwarp();
+    st = (st + 1) % STAGES;
+  }
+  out[1 + blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
 
 template <typename F>
@@ -206,6 +261,18 @@ int main(int argc, char** argv) {
     timeit("E ld256 G=5 160B rows UN=4", n, [&] { k_group256<5, 4><<<148 * 8, 256>>>(table, idx, n, out); });
     timeit("E ld256 G=10 320B rows UN=4 (n/2 rows)", n / 2, [&] { k_group256<10, 4><<<148 * 12, 256>>>(t2, idx, n / 2, out); });
     timeit("E ld256 G=10 320B rows UN=8 (n/2 rows)", n / 2, [&] { k_group256<10, 8><<<148 * 8, 256>>>(t2, idx, n / 2, out); });
+  }
+  {
+    double* t2; CK(cudaMalloc(&t2, nrows * 320)); CK(cudaMemset(t2, 0, nrows * 320));
+#define RUN_F(W, ST, UNv, OCC)                                                                          \
+    {                                                                                                   \
+      size_t smem = (size_t)W * ST * (UNv * 3) * 320 + W * ST * 8;                                      \
+      CK(cudaFuncSetAttribute(k_tma_pair<W, ST, UNv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      char nm[96]; snprintf(nm, sizeof nm, "F tma pair %dw st%d un%d x%d/SM (n/2 rows)", W, ST, UNv, OCC); \
+      timeit(nm, n / 2, [&] { k_tma_pair<W, ST, UNv><<<148 * OCC, W * 32, smem>>>(t2, idx, n / 2, out); }); \
+    }
+    RUN_F(8, 2, 3, 3) RUN_F(8, 3, 3, 3) RUN_F(8, 4, 3, 2) RUN_F(8, 3, 3, 4) RUN_F(8, 4, 3, 4)
+    RUN_F(8, 3, 4, 3) RUN_F(8, 3, 8, 2) RUN_F(16, 3, 3, 2) RUN_F(8, 6, 3, 2)
   }
   timeit("C ld256 lane/row", n, [&] { k_lane<true><<<148 * 8, 256>>>(table, idx, n, out); });
   timeit("D ld128 lane/row", n, [&] { k_lane<false><<<148 * 8, 256>>>(table, idx, n, out); });
