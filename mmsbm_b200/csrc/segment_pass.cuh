@@ -348,14 +348,14 @@ segment_pass_kernel(const SegArgs A) {
               }
             }
           };
-          if (cnt > (UN - 1) * RPS) chunk(std::integral_constant<int, UN>{});
-          else if constexpr (UN >= 2) {
-            if (UN == 2 || cnt <= RPS) chunk(std::integral_constant<int, 1>{});
-            else if constexpr (UN >= 3) {
-              if (UN == 3 || cnt <= 2 * RPS) chunk(std::integral_constant<int, 2>{});
-              else if constexpr (UN >= 4) chunk(std::integral_constant<int, 3>{});
-            }
-          }
+          static_assert(UN <= 6, "extend the step-count dispatch");
+          const int ns = (cnt + RPS - 1) / RPS;  // steps that hold ratings, 1..UN (warp-uniform)
+          if (ns == UN) chunk(std::integral_constant<int, UN>{});
+          else if (ns == 1) chunk(std::integral_constant<int, 1>{});
+          else if (UN > 2 && ns == 2) chunk(std::integral_constant<int, (UN > 2 ? 2 : 1)>{});
+          else if (UN > 3 && ns == 3) chunk(std::integral_constant<int, (UN > 3 ? 3 : 1)>{});
+          else if (UN > 4 && ns == 4) chunk(std::integral_constant<int, (UN > 4 ? 4 : 1)>{});
+          else if (UN > 5 && ns == 5) chunk(std::integral_constant<int, (UN > 5 ? 5 : 1)>{});
         }
         lo = le;
       }
