@@ -60,6 +60,16 @@ def _distinct_strings(col):
     return codes, uniq.tolist()
 
 
+def _distinct_strings_all(cols):
+    """``_distinct_strings`` of several columns; the hash passes run in threads for long columns
+    (pandas' factorize releases the GIL)."""
+    if len(cols) > 1 and len(cols[0]) >= 100_000:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(len(cols)) as ex:
+            return list(ex.map(_distinct_strings, cols))
+    return [_distinct_strings(c) for c in cols]
+
+
 def _rank_table(strings):
     """{string: rank in sorted(set(strings))} (src/data_handler.py:39-44)."""
     return {s: k for k, s in enumerate(sorted(set(strings.tolist())))}
@@ -147,8 +157,7 @@ class DataHandler:
         #  where no cell is null any more: it cannot fire, so there is nothing to check here)
         out = np.empty((len(data), 3), dtype=np.int64)
         tables = []
-        for c in range(3):
-            codes, strings = _distinct_strings(data.iloc[:, c])
+        for c, (codes, strings) in enumerate(_distinct_strings_all([data.iloc[:, c] for c in range(3)])):
             table = {s: k for k, s in enumerate(sorted(set(strings)))}
             lut = np.array([table[s] for s in strings], dtype=np.int64)
             out[:, c] = lut[codes] if len(codes) else 0
@@ -182,9 +191,10 @@ class DataHandler:
         logger = logging.getLogger("MMSBM")
         alive = np.ones(len(data), dtype=bool)
         enc = np.empty((len(data), 3), dtype=np.int64)
+        parts = _distinct_strings_all([data[c] for c in ("users", "items", "ratings")])
         for c, (column, table) in enumerate((("users", self.obs_dict), ("items", self.items_dict),
                                              ("ratings", self.ratings_dict))):
-            codes, strings = _distinct_strings(data[column])
+            codes, strings = parts[c]
             lut = np.array([table.get(s, -1) for s in strings], dtype=np.int64)
             present = np.zeros(len(strings), dtype=bool)
             present[codes[alive]] = True                      # distinct values among the rows still there

@@ -83,7 +83,7 @@ class MMSBM:
     def _prepare_objects(self, train):
         """Sizes, degree factors and the on-device index structure
         (replaces src/mmsbm.py:93-146; the O((U+I)N) scans become one GPU sort)."""
-        self.ratings = sorted(set(train[:, 2]))
+        self.ratings = list(np.unique(train[:, 2]))          # = sorted(set(train[:, 2])), src/mmsbm.py:95
         self.r = max(self.ratings)
         self.p = int(train[:, 0].max())
         self.m = int(train[:, 1].max())
