@@ -488,14 +488,21 @@ static PassShape choose_shape(int NBp, double avg_degree) {
   return sh;
 }
 
-static int segs_per_cta_for(int nseg) {
-  // dynamic scheduling inside a CTA needs several segments per warp to balance; keep >= ~600
-  // CTAs per run so that the grid still covers 148 SMs x 3 several times over
-  int spc = nseg / 592;
-  if (spc < kWarps) spc = kWarps;               // small problems: one segment per warp, most CTAs
-  if (spc > 64) spc = 64;
+// Pieces per CTA, a multiple of the warps per CTA (the warps claim pieces dynamically; with 9
+// pieces for 8 warps the CTA would last two piece times).  Two rules from the sweep in
+// profiles/r1_spc_sweep.txt: about 6k ratings of work per CTA -- short segments want several per
+// warp to even out, long pieces want one per warp so that the last wave of CTAs is short -- and
+// at least ~6 CTAs per resident slot (148 SMs x 3) whatever the problem size.
+static int segs_per_cta_for(int64_t pmax, int64_t n_ratings, int grid_y) {
   const int e = env_int("MMSBM_SPC", 0);
-  return e > 0 ? e : spc;
+  if (e > 0) return e;
+  const double avg_piece = (double)(n_ratings > 0 ? n_ratings : 1) / (double)(pmax > 0 ? pmax : 1);
+  int64_t spc = ((int64_t)(6144.0 / (avg_piece > 1.0 ? avg_piece : 1.0)) + kWarps / 2) / kWarps * kWarps;
+  const int64_t fill = pmax * grid_y / (148 * 3 * 6) / kWarps * kWarps;
+  if (spc > fill) spc = fill;
+  if (spc < kWarps) spc = kWarps;               // one piece per warp at least
+  if (spc > 64) spc = 64;
+  return (int)spc;
 }
 
 // pairs of runs per warp whenever there are at least two runs and a lane holds one chunk
@@ -507,9 +514,6 @@ static int launch_segment_pass_impl(SegArgs a, const double* nbr_pairs, int64_t 
                                     cudaStream_t st) {
   const double avg_degree = (double)n_ratings / (double)a.nseg;
   PassShape sh = choose_shape(a.NBp, avg_degree);
-  a.segs_per_cta = segs_per_cta_for(a.nseg);
-  // the piece count lives on the device; size the grid for its upper bound (CTAs past it exit)
-  const unsigned gx = (unsigned)((a.pmax + a.segs_per_cta - 1) / a.segs_per_cta);
   const int un_e = env_int("MMSBM_UN", 0), occ_e = env_int("MMSBM_OCC", 0);
   int single_from = 0;                           // runs [single_from, n_runs) go one run per warp
   if (nbr_pairs && pairs_enabled(a.NBp, n_runs)) {
@@ -517,6 +521,9 @@ static int launch_segment_pass_impl(SegArgs a, const double* nbr_pairs, int64_t 
     SegArgs p = a;
     p.nbr = nbr_pairs;
     p.run_base = 0;
+    p.segs_per_cta = segs_per_cta_for(a.pmax, n_ratings, pairs);
+    // the piece count lives on the device; size the grid for its upper bound (CTAs past it exit)
+    const unsigned gx = (unsigned)((a.pmax + p.segs_per_cta - 1) / p.segs_per_cta);
     const size_t smem = seg_smem_bytes(p, 2);
     MMSBM_REQUIRE(smem <= 227 * 1024, MMSBM_ERANGE, "segment pass needs %zu bytes of shared memory", smem);
     int UN = (sh.G == 1) ? 2 : 3, MINB = 3;                     // UN * (32 / 2G) <= 32
@@ -533,6 +540,8 @@ static int launch_segment_pass_impl(SegArgs a, const double* nbr_pairs, int64_t 
     if (single_from == n_runs) return 0;
   }
   a.run_base = single_from;
+  a.segs_per_cta = segs_per_cta_for(a.pmax, n_ratings, n_runs - single_from);
+  const unsigned gx = (unsigned)((a.pmax + a.segs_per_cta - 1) / a.segs_per_cta);
   const dim3 grid(gx, n_runs - single_from);
   const size_t smem = seg_smem_bytes(a, 1);
   MMSBM_REQUIRE(smem <= 227 * 1024, MMSBM_ERANGE,
