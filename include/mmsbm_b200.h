@@ -54,7 +54,9 @@ extern "C" {
 
 /* a warp of the hot kernel processes at most this many ratings of one segment at a time; longer
  * segments are cut into pieces whose partial sums are added in piece order (see usched/isched) */
+#ifndef MMSBM_PIECE_LEN
 #define MMSBM_PIECE_LEN 2048
+#endif
 
 #define MMSBM_EINVAL  (-1)   /* bad argument (null pointer, size out of range)      */
 #define MMSBM_ERANGE  (-2)   /* shape not supported (K or L > 256, R > 31, id*R >= 2^31) */
