@@ -195,3 +195,23 @@ def test_fold_construction_matches_reference(golden_dir, case):
         assert [hashlib.sha1(",".join(str(a) for a in tr.index).encode()).hexdigest() for tr, _ in pairs] \
             == want["train_sha1"]
         assert float(m.rng.random()) == want["next_random"]
+
+
+def test_encoding_threaded_hash_passes_match_serial():
+    """Columns of >= 100k rows are factorised in threads (data_handler._distinct_strings_all)."""
+    from mmsbm_b200 import data_handler as dhm
+    rng = np.random.default_rng(11)
+    n = 120_000
+    df = pd.DataFrame({"users": rng.integers(0, 5000, n), "items": ["i%d" % x for x in rng.integers(0, 900, n)],
+                       "ratings": rng.choice([0.5, 1.0, 2.5, 4.0], n)})
+    fast = DataHandler()
+    out = fast.format_train_data(df)
+    cols = [df.iloc[:, c] for c in range(3)]
+    for (codes, strings), col in zip(dhm._distinct_strings_all(cols), cols):
+        c2, s2 = dhm._distinct_strings(col)
+        np.testing.assert_array_equal(codes, c2)
+        assert strings == s2
+    slow = DataHandler()
+    np.testing.assert_array_equal(slow.parse_train_data(slow._to_object_str(df.iloc[:20000].copy())),
+                                  DataHandler().format_train_data(df.iloc[:20000]))
+    assert out.shape == (n, 3) and out[:, 0].max() == len(fast.obs_dict) - 1
