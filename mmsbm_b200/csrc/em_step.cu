@@ -63,19 +63,19 @@ __global__ void __launch_bounds__(128) segment_fixup_kernel(const SegArgs A) {
   }
 }
 
-// ---- rows of run pairs interleaved: dst[pair][id][2][ld] <- src[2*pair + {0,1}][id][ld] --------
-__global__ void interleave_pairs_kernel(const double* __restrict__ src, double* __restrict__ dst, int n,
-                                        int ld, int pairs) {
+// ---- rows of run groups interleaved: dst[grp][id][j][ld] <- src[gs*grp + j][id][ld], j < gs ------
+__global__ void interleave_runs_kernel(const double* __restrict__ src, double* __restrict__ dst, int n,
+                                       int ld, int groups, int gs) {
   const int c4 = ld >> 2;
-  const size_t total = (size_t)pairs * n * 2 * c4;
+  const size_t total = (size_t)groups * n * gs * c4;
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int c = (int)(t % c4);
-  const int rs = (int)((t / c4) & 1);
-  const size_t rest = t / c4 / 2;
+  const int j = (int)((t / c4) % gs);
+  const size_t rest = t / c4 / gs;
   const int id = (int)(rest % n);
   const size_t p = rest / n;
-  const double4_t v = ldg256(src + (((size_t)(2 * p + rs) * n + id) * ld + 4 * c));
+  const double4_t v = ldg256(src + (((size_t)(gs * p + j) * n + id) * ld + 4 * c));
   stg256(dst + 4 * t, v);
 }
 
@@ -510,17 +510,44 @@ static bool pairs_enabled(int NBp, int n_runs) {
   return n_runs >= 2 && NBp <= 32 && env_int("MMSBM_PAIR", 1) != 0;
 }
 
-static int launch_segment_pass_impl(SegArgs a, const double* nbr_pairs, int64_t n_ratings, int n_runs,
-                                    cudaStream_t st) {
+// six runs per warp: rows of exactly 20 doubles (5-lane groups, 30 of 32 lanes), at least six runs
+static bool hexa_enabled(int NBp, int n_runs) {
+  return n_runs >= 6 && NBp == 20 && env_int("MMSBM_HEXA", 1) != 0;
+}
+
+static int launch_segment_pass_impl(SegArgs a, const double* nbr_pairs, const double* nbr_hexa,
+                                    int64_t n_ratings, int n_runs, cudaStream_t st) {
   const double avg_degree = (double)n_ratings / (double)a.nseg;
   PassShape sh = choose_shape(a.NBp, avg_degree);
   const int un_e = env_int("MMSBM_UN", 0), occ_e = env_int("MMSBM_OCC", 0);
   int single_from = 0;                           // runs [single_from, n_runs) go one run per warp
-  if (nbr_pairs && pairs_enabled(a.NBp, n_runs)) {
-    const int pairs = n_runs / 2;
+  if (nbr_hexa && hexa_enabled(a.NBp, n_runs)) {
+    const int hexas = n_runs / 6;
+    SegArgs p = a;
+    p.nbr = nbr_hexa;
+    p.run_base = 0;
+    p.grp_base = 0;
+    p.segs_per_cta = segs_per_cta_for(a.pmax, n_ratings, hexas);
+    const unsigned gx = (unsigned)((a.pmax + p.segs_per_cta - 1) / p.segs_per_cta);
+    const size_t smem = seg_smem_bytes(p, 6);
+    MMSBM_REQUIRE(smem <= 227 * 1024, MMSBM_ERANGE, "segment pass needs %zu bytes of shared memory", smem);
+    int rc = MMSBM_ERANGE;
+    if (un_e > 0 || occ_e > 0)
+      rc = launch_segment_pass_hexa(p, sh.G, un_e > 0 ? un_e : 3, occ_e > 0 ? occ_e : 3, dim3(gx, hexas), smem, st);
+    if (rc == MMSBM_ERANGE) rc = launch_segment_pass_hexa(p, sh.G, 3, 3, dim3(gx, hexas), smem, st);
+    if (rc) {
+      if (rc == MMSBM_ERANGE) set_error("no six-run segment-pass variant for G=%d", sh.G);
+      return rc;
+    }
+    single_from = 6 * hexas;
+    if (single_from == n_runs) return 0;
+  }
+  if (nbr_pairs && pairs_enabled(a.NBp, n_runs - single_from)) {
+    const int pairs = (n_runs - single_from) / 2;
     SegArgs p = a;
     p.nbr = nbr_pairs;
-    p.run_base = 0;
+    p.run_base = single_from;
+    p.grp_base = single_from / 2;                // pairs are numbered over all runs (6 | single_from)
     p.segs_per_cta = segs_per_cta_for(a.pmax, n_ratings, pairs);
     // the piece count lives on the device; size the grid for its upper bound (CTAs past it exit)
     const unsigned gx = (unsigned)((a.pmax + p.segs_per_cta - 1) / p.segs_per_cta);
@@ -536,7 +563,7 @@ static int launch_segment_pass_impl(SegArgs a, const double* nbr_pairs, int64_t 
       if (rc == MMSBM_ERANGE) set_error("no paired segment-pass variant for G=%d", sh.G);
       return rc;
     }
-    single_from = 2 * pairs;
+    single_from += 2 * pairs;
     if (single_from == n_runs) return 0;
   }
   a.run_base = single_from;
@@ -567,9 +594,9 @@ static int launch_segment_pass_impl(SegArgs a, const double* nbr_pairs, int64_t 
   return rc;
 }
 
-static int launch_segment_pass_and_fixup(SegArgs a, const double* nbr_pairs, int64_t n_ratings, int n_runs,
-                                         cudaStream_t st) {
-  int rc = launch_segment_pass_impl(a, nbr_pairs, n_ratings, n_runs, st);
+static int launch_segment_pass_and_fixup(SegArgs a, const double* nbr_pairs, const double* nbr_hexa,
+                                         int64_t n_ratings, int n_runs, cudaStream_t st) {
+  int rc = launch_segment_pass_impl(a, nbr_pairs, nbr_hexa, n_ratings, n_runs, st);
   if (rc) return rc;
   const unsigned gx = (unsigned)(a.lmax < 592 ? a.lmax : 592);
   segment_fixup_kernel<<<dim3(gx, n_runs), 128, 0, st>>>(a);
@@ -656,6 +683,7 @@ struct EmDims {
   int nseg_e, NA_e, NBp_e;
   size_t p_elems, wg_u_elems, wg_i_elems, partial_elems, slots_u_elems, slots_i_elems;
   size_t th2_elems, et2_elems;   // theta / eta with the rows of run pairs interleaved
+  size_t et6_elems;              // eta with the rows of groups of six runs interleaved (by-user pass)
   int64_t lmax, smax, pmax_u, pmax_i;
 };
 
@@ -680,6 +708,7 @@ static EmDims em_dims(int64_t N, int U, int I, int R, int K, int L, int S) {
   d.slots_i_elems = (size_t)S * d.smax * d.rnb_i;
   d.th2_elems = (size_t)(S / 2) * 2 * U * d.ldk;
   d.et2_elems = (size_t)(S / 2) * 2 * I * d.ldl;
+  d.et6_elems = (size_t)(S / 6) * 6 * I * d.ldl;
   return d;
 }
 
@@ -694,7 +723,7 @@ extern "C" int mmsbm_em_workspace_bytes(int64_t N, int32_t U, int32_t I, int32_t
   EmDims d = em_dims(N, U, I, R, K, L, S);
   *bytes = 4 * align_up(d.p_elems * 8) + align_up(d.wg_u_elems * 8) + align_up(d.wg_i_elems * 8) +
            align_up(d.partial_elems * 8) + align_up(d.slots_u_elems * 8) + align_up(d.slots_i_elems * 8) +
-           align_up(d.th2_elems * 8) + align_up(d.et2_elems * 8) + 256;
+           align_up(d.th2_elems * 8) + align_up(d.et2_elems * 8) + align_up(d.et6_elems * 8) + 256;
   return 0;
 }
 
@@ -733,7 +762,8 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
   double* slots_i = arena.take<double>(d.slots_i_elems);
   double* th2 = arena.take<double>(d.th2_elems);
   double* et2 = arena.take<double>(d.et2_elems);
-  MMSBM_REQUIRE(pw_u && pn_u && pw_i && pn_i && wg_u && wg_i && partial && slots_u && slots_i && th2 && et2,
+  double* et6 = arena.take<double>(d.et6_elems);
+  MMSBM_REQUIRE(pw_u && pn_u && pw_i && pn_i && wg_u && wg_i && partial && slots_u && slots_i && th2 && et2 && et6,
                 MMSBM_ENOMEM,
                 "mmsbm_em_step: workspace too small (%zu)", ws_bytes);
   int rc;
@@ -751,15 +781,20 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
     prep_p_kernel<<<dim3((total + 255) / 256, S), 256, 0, st>>>(pr, K, L, R, d.ldk, d.ldl, pw_u, pn_u, pw_i, pn_i);
     MMSBM_LAUNCH_CHECK("prep_p_kernel");
     MMSBM_FORK(0);                                                  // side: after the P tables
-    if (pairs_enabled(d.ldl, S)) {     // eta rows of run pairs side by side (by-user pass gathers)
+    if (hexa_enabled(d.ldl, S)) {      // eta rows of six runs side by side (by-user pass gathers)
+      const size_t tot = (size_t)(S / 6) * I * 6 * (d.ldl / 4);
+      interleave_runs_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(eta, et6, I, d.ldl, S / 6, 6);
+      MMSBM_LAUNCH_CHECK("interleave_runs_kernel");
+    }
+    if (pairs_enabled(d.ldl, S)) {     // eta rows of run pairs side by side
       const size_t tot = (size_t)(S / 2) * I * 2 * (d.ldl / 4);
-      interleave_pairs_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(eta, et2, I, d.ldl, S / 2);
-      MMSBM_LAUNCH_CHECK("interleave_pairs_kernel");
+      interleave_runs_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(eta, et2, I, d.ldl, S / 2, 2);
+      MMSBM_LAUNCH_CHECK("interleave_runs_kernel");
     }
     if (pairs_enabled(d.ldk, S)) {     // theta rows likewise (by-item pass gathers)
       const size_t tot = (size_t)(S / 2) * U * 2 * (d.ldk / 4);
-      interleave_pairs_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(theta, th2, U, d.ldk, S / 2);
-      MMSBM_LAUNCH_CHECK("interleave_pairs_kernel");
+      interleave_runs_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(theta, th2, U, d.ldk, S / 2, 2);
+      MMSBM_LAUNCH_CHECK("interleave_runs_kernel");
     }
     if ((rc = launch_w(theta, pw_u, wg_u, U, d.ldk, d.rnb_u, S, st))) return rc;
     if ((rc = launch_w(eta, pw_i, wg_i, I, d.ldl, d.rnb_i, S, s2))) return rc;
@@ -769,7 +804,7 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
   // ---- by-user pass: g of every user (gathers eta rows) ----
   {
     SegArgs a{useg, uadj, usched, eta, wg_u, slots_u, d.pmax_u, d.lmax, d.smax, U, I, d.ldl, R, 0, 0};
-    if ((rc = launch_segment_pass_and_fixup(a, et2, N, S, st))) return rc;
+    if ((rc = launch_segment_pass_and_fixup(a, et2, et6, N, S, st))) return rc;
   }
   MMSBM_MARK(2);
   // theta' = (g x Pn) o theta / max(deg,1): off the critical path, overlaps the by-item pass
@@ -782,7 +817,8 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
   if (ov) MMSBM_CUDA(cudaStreamWaitEvent(st, ov->e[1], 0));
   {
     SegArgs a{iseg, iadj, isched, theta, wg_i, slots_i, d.pmax_i, d.lmax, d.smax, I, U, d.ldk, R, 0, 0};
-    if ((rc = launch_segment_pass_and_fixup(a, th2, N, S, st))) return rc;
+    // (pairs only: six interleaved theta tables of 138k users would not fit L2)
+    if ((rc = launch_segment_pass_and_fixup(a, th2, nullptr, N, S, st))) return rc;
   }
   MMSBM_MARK(4);
   // eta' likewise; overlaps the pr kernels

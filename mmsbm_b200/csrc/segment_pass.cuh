@@ -68,16 +68,20 @@ struct SegArgs {
   const int32_t* seg;   // [nseg*R+1]
   const int32_t* adj;   // [N] neighbour ids, grouped by (segment, level)
   const int32_t* sched; // work schedule: pieces of <= MMSBM_PIECE_LEN ratings (graph_build.cu)
-  const double* nbr;    // RUNS == 1: [S][nnbr][NBp]   RUNS == 2: [S/2][nnbr][2][NBp] (runs interleaved)
+  const double* nbr;    // RUNS == 1: [S][nnbr][NBp]   RUNS > 1: [groups][nnbr][RUNS][NBp] (runs interleaved)
   double* wg;           // [S][nseg][R*NBp]  in: w   out: g (in place; single-piece segments)
   double* partial;      // [S][smax][R*NBp]  out: g of the pieces of long segments, by slot
   int64_t pmax, lmax, smax;   // capacities: pieces, long segments, slots (graph_build.cu)
   int nseg, nnbr, NBp, R, segs_per_cta;
-  int run_base;         // first run of this launch (grid.y counts runs, or pairs of runs)
+  int run_base;         // first run of this launch (grid.y counts runs, or groups of RUNS runs)
+  int grp_base;         // RUNS > 1: first run group of this launch inside nbr
 };
 
+// w rows in shared memory: double buffered (next piece's rows land while this piece runs) for
+// one run or a pair per warp, single buffered for wider run groups (6 runs: 77 KB per CTA otherwise)
+__host__ __device__ constexpr int w_buffers(int runs) { return runs > 2 ? 1 : 2; }
 inline size_t seg_smem_bytes(const SegArgs& a, int runs) {
-  return (size_t)kWarps * 2 * runs * a.R * a.NBp * 8 + 32;
+  return (size_t)kWarps * w_buffers(runs) * runs * a.R * a.NBp * 8 + 32;
 }
 
 // Sum of `part` over the G consecutive lanes of a group, delivered to every lane of the group.
@@ -158,6 +162,8 @@ struct GroupSum {
   }
 };
 
+// RUNS == 6 (5-lane groups only, by-user pass): six runs fill the warp (30 lanes), one rating per
+// step -- no cross-group reduction when a level is flushed, a 960-byte contiguous gather.
 // RUNS == 2: a warp serves the same piece for a PAIR of runs.  The neighbour rows of the two
 // runs are interleaved in memory, so a rating's gather is one contiguous 2*8*NB-byte read
 // (fewer L1 wavefronts per byte than two separate rows), and the index loads, the level
@@ -175,8 +181,9 @@ segment_pass_kernel(const SegArgs A) {
   const int R = A.R, NBp = (CH == 1) ? 4 * G : A.NBp, RNB = R * NBp;
   const int NCH = NBp >> 2;                      // 32-byte chunks per neighbour row
 
-  double* wbuf = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 2 * RUNS * RNB;   // [2][RUNS][RNB]
-  int* ctr = reinterpret_cast<int*>(smem_raw + (size_t)kWarps * 2 * RUNS * RNB * 8);
+  constexpr int WB = w_buffers(RUNS);
+  double* wbuf = reinterpret_cast<double*>(smem_raw) + (size_t)warp * WB * RUNS * RNB;  // [WB][RUNS][RNB]
+  int* ctr = reinterpret_cast<int*>(smem_raw + (size_t)kWarps * WB * RUNS * RNB * 8);
   if (threadIdx.x == 0) *ctr = kWarps;           // warps start on segments 0..kWarps-1
   __syncthreads();
 
@@ -193,7 +200,7 @@ segment_pass_kernel(const SegArgs A) {
   const int seg_hi = min(seg_lo + A.segs_per_cta, n_pieces);
   // base of this lane's neighbour rows: row(id) = nbr_run + id * RUNS * NBp
   const double* nbr_run = (RUNS == 1) ? A.nbr + (size_t)run * A.nnbr * NBp
-                                      : A.nbr + ((size_t)blockIdx.y * A.nnbr * RUNS + rsel) * NBp;
+                                      : A.nbr + ((size_t)(A.grp_base + blockIdx.y) * A.nnbr * RUNS + rsel) * NBp;
   int coff[CH];                                  // lane-constant chunk offsets (in doubles)
   bool con[CH];
 #pragma unroll
@@ -225,7 +232,7 @@ segment_pass_kernel(const SegArgs A) {
     MMSBM_DEV_CHECK(sg_out >= 0 && sg_out < A.nseg);
     pinfo_pref = (lane == 0) ? __ldg(piece_idx + p_) : (lane == 1) ? __ldg(piece_slot + p_) : 0;
     if (lane <= R) bend_pref = __ldg(A.seg + (size_t)sg_out * R + lane);
-    fetch_w(sg_out, b_);
+    if constexpr (WB == 2) fetch_w(sg_out, b_);
   };
   if (pi < seg_hi) prefetch_piece(pi, 0, sg);
   cp_async_commit();
@@ -246,9 +253,15 @@ segment_pass_kernel(const SegArgs A) {
     // ids of the first chunk; slots past the end read row 0 (in bounds, weight zero)
     int cur_ids = 0;
     if (lane < SLOTS && beg + lane < end) cur_ids = ld_stream(A.adj + beg + lane);
-    cp_async_wait<1>();                          // this segment's w has landed
+    if constexpr (WB == 2) {
+      cp_async_wait<1>();                        // this segment's w has landed
+    } else {                                     // single buffer: fetched now (the previous piece is done with it)
+      fetch_w(sg, 0);
+      cp_async_commit();
+      cp_async_wait<0>();
+    }
     __syncwarp();
-    const double* wb = wbuf + (size_t)(buf * RUNS + rsel) * RNB;
+    const double* wb = wbuf + (size_t)((WB == 2 ? buf : 0) * RUNS + rsel) * RNB;
     double* gout = (slot < 0) ? A.wg + ((size_t)run * A.nseg + sg) * RNB
                               : A.partial + ((size_t)run * A.smax + slot) * RNB;
 
@@ -372,6 +385,7 @@ segment_pass_kernel(const SegArgs A) {
 // one instantiation unit per CH (seg_inst_ch*.cu) keeps compile time parallel
 int launch_segment_pass_ch1(const SegArgs& a, int G, int UN, int MINB, dim3 grid, size_t smem, cudaStream_t st);
 int launch_segment_pass_pair(const SegArgs& a, int G, int UN, int MINB, dim3 grid, size_t smem, cudaStream_t st);
+int launch_segment_pass_hexa(const SegArgs& a, int G, int UN, int MINB, dim3 grid, size_t smem, cudaStream_t st);
 int launch_segment_pass_ch2(const SegArgs& a, int G, int UN, int MINB, dim3 grid, size_t smem, cudaStream_t st);
 int launch_segment_pass_ch4(const SegArgs& a, int G, int UN, int MINB, dim3 grid, size_t smem, cudaStream_t st);
 int launch_segment_pass_ch8(const SegArgs& a, int G, int UN, int MINB, dim3 grid, size_t smem, cudaStream_t st);

@@ -147,7 +147,8 @@ def test_fixture_one_and_ten_iterations(golden_dir):
 
 
 @pytest.mark.parametrize("K,L,R,S", [(10, 10, 5, 3), (20, 20, 5, 2), (7, 5, 4, 1), (3, 32, 6, 2), (33, 9, 5, 1),
-                                     (1, 1, 2, 1), (64, 48, 5, 1), (130, 70, 3, 1), (12, 28, 10, 2), (20, 20, 5, 5)])
+                                     (1, 1, 2, 1), (64, 48, 5, 1), (130, 70, 3, 1), (12, 28, 10, 2), (20, 20, 5, 5),
+                                     (20, 20, 5, 8), (7, 18, 4, 7), (20, 19, 3, 13)])
 @pytest.mark.parametrize("heavy", [False, True])
 def test_batched_runs_one_iteration_vs_oracle(K, L, R, S, heavy):
     from mmsbm_b200.engine import Engine
