@@ -75,6 +75,8 @@ struct SegArgs {
   int nseg, nnbr, NBp, R, segs_per_cta;
   int run_base;         // first run of this launch (grid.y counts runs, or groups of RUNS runs)
   int grp_base;         // RUNS > 1: first run group of this launch inside nbr
+  int* counters;        // [gridDim.y] zeroed by the host: pieces are claimed across the whole launch
+                        // (persistent CTAs); NULL: every CTA owns segs_per_cta consecutive pieces
 };
 
 // w rows in shared memory: double buffered (next piece's rows land while this piece runs) for
@@ -184,7 +186,7 @@ segment_pass_kernel(const SegArgs A) {
   constexpr int WB = w_buffers(RUNS);
   double* wbuf = reinterpret_cast<double*>(smem_raw) + (size_t)warp * WB * RUNS * RNB;  // [WB][RUNS][RNB]
   int* ctr = reinterpret_cast<int*>(smem_raw + (size_t)kWarps * WB * RUNS * RNB * 8);
-  if (threadIdx.x == 0) *ctr = kWarps;           // warps start on segments 0..kWarps-1
+  if (threadIdx.x == 0) *ctr = 0;
   __syncthreads();
 
   const int grp = lane / GR, lig = lane - grp * GR;
@@ -196,8 +198,16 @@ segment_pass_kernel(const SegArgs A) {
   const int32_t* piece_idx = piece_seg + A.pmax;
   const int32_t* piece_slot = piece_idx + A.pmax;
   const int n_pieces = __ldg(A.sched);
-  const int seg_lo = blockIdx.x * A.segs_per_cta;
-  const int seg_hi = min(seg_lo + A.segs_per_cta, n_pieces);
+  // A warp starts on piece `first` and claims further ones with an atomic counter: claim t is
+  // piece claim_base + t.  With A.counters the counter is global to the launch (one per grid.y),
+  // every warp of the grid draws from the same queue, so no CTA is left with a long tail whatever
+  // the lengths of the pieces; otherwise the counter is per CTA over its own range of pieces.
+  const bool dyn = A.counters != nullptr;
+  int* claim = dyn ? A.counters + blockIdx.y : ctr;
+  const int seg_lo = dyn ? 0 : blockIdx.x * A.segs_per_cta;
+  const int seg_hi = dyn ? n_pieces : min(seg_lo + A.segs_per_cta, n_pieces);
+  const int first = dyn ? blockIdx.x * kWarps + warp : seg_lo + warp;
+  const int claim_base = dyn ? gridDim.x * kWarps : seg_lo + kWarps;
   // base of this lane's neighbour rows: row(id) = nbr_run + id * RUNS * NBp
   const double* nbr_run = (RUNS == 1) ? A.nbr + (size_t)run * A.nnbr * NBp
                                       : A.nbr + ((size_t)(A.grp_base + blockIdx.y) * A.nnbr * RUNS + rsel) * NBp;
@@ -224,7 +234,7 @@ segment_pass_kernel(const SegArgs A) {
 
   // prefetched state of a piece: its segment, (piece number, slot) in lanes 0 and 1, and the
   // level boundaries of the segment (lane r <= R holds the start of level r)
-  int pi = seg_lo + warp, buf = 0;
+  int pi = first, buf = 0;
   int sg = 0, pinfo_pref = 0, bend_pref = 0;
   auto prefetch_piece = [&](int p_, int b_, int& sg_out) {
     MMSBM_DEV_CHECK(p_ >= 0 && p_ < A.pmax);
@@ -241,8 +251,8 @@ segment_pass_kernel(const SegArgs A) {
     const int bend_reg = bend_pref, pinfo = pinfo_pref;
     // claim the next piece, start fetching its descriptors and its w row
     int t = 0;
-    if (lane == 0) t = atomicAdd(ctr, 1);
-    const int pi_next = seg_lo + __shfl_sync(kFull, t, 0);
+    if (lane == 0) t = atomicAdd(claim, 1);
+    const int pi_next = claim_base + __shfl_sync(kFull, t, 0);
     int sg_next = 0;
     if (pi_next < seg_hi) prefetch_piece(pi_next, buf ^ 1, sg_next);
     cp_async_commit();
