@@ -300,10 +300,14 @@ def test_launch_strategies_give_identical_bits(monkeypatch):
     data = random_triples(83, 80000, 900, 500, 5, heavy_tail=True)
     theta, eta, pr = random_params(89, 900, 500, 12, 9, 5, S=3)
     outs = {}
-    for name, env in (("plain", {"MMSBM_NO_GRAPH": "1", "MMSBM_NO_OVERLAP": "1"}),
+    for name, env in (("plain", {"MMSBM_NO_GRAPH": "1", "MMSBM_NO_OVERLAP": "1", "MMSBM_DYN": "0"}),
                       ("graph", {"MMSBM_NO_OVERLAP": "1"}),
-                      ("overlap", {"MMSBM_FORCE_OVERLAP": "1"})):
-        for k in ("MMSBM_NO_GRAPH", "MMSBM_NO_OVERLAP", "MMSBM_FORCE_OVERLAP"):
+                      ("overlap", {"MMSBM_FORCE_OVERLAP": "1"}),
+                      # launch-wide piece queue (persistent CTAs), plain and inside the CUDA graph
+                      ("queue", {"MMSBM_NO_GRAPH": "1", "MMSBM_NO_OVERLAP": "1", "MMSBM_DYN": "1"}),
+                      ("queue+graph", {"MMSBM_NO_OVERLAP": "1", "MMSBM_DYN": "1"}),
+                      ("queue+overlap", {"MMSBM_FORCE_OVERLAP": "1", "MMSBM_DYN": "1"})):
+        for k in ("MMSBM_NO_GRAPH", "MMSBM_NO_OVERLAP", "MMSBM_FORCE_OVERLAP", "MMSBM_DYN"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -311,7 +315,7 @@ def test_launch_strategies_give_identical_bits(monkeypatch):
         e.set_params(theta, eta, pr)
         e.run(11)
         outs[name] = e.get_params() + (e.likelihood(),)
-    for name in ("graph", "overlap"):
+    for name in ("graph", "overlap", "queue", "queue+graph", "queue+overlap"):
         for a, b in zip(outs["plain"], outs[name]):
             np.testing.assert_array_equal(a, b, err_msg=name)
 
