@@ -5,5 +5,5 @@ python bench.py --workload netflix --iters-per-step 100 --no-cpu > gpurun_out/be
 python bench.py --workload ml100k --iters-per-step 200 --no-cpu > gpurun_out/bench_ml100k.json 2> gpurun_out/bench_ml100k.err
 python bench.py --ids zipf --iters-per-step 100 --no-cpu > gpurun_out/bench_zipf.json 2> gpurun_out/bench_zipf.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1_v13.csv python bench.py --steps 1 --warmup 1 --iters-per-step 2 --no-e2e --no-cpu > gpurun_out/ncu_list.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:segment_pass --launch-skip 4 -c 2 -f -o gpurun_out/prof_r1_v13 python bench.py --steps 1 --warmup 1 --iters-per-step 2 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:segment_pass --launch-skip 3 -c 3 -f -o gpurun_out/prof_r1_v13 python bench.py --steps 1 --warmup 1 --iters-per-step 2 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1
 echo done
