@@ -16,6 +16,9 @@
 //
 // Kernels of one iteration (all runs in grid.y, run-major so one run's tables stay in L2):
 //   prep_p_kernel        P in the two operand layouts of each side
+//   interleave_runs_kernel  theta / eta rows of run groups side by side (pairs; six runs for eta
+//                        rows of 20 doubles): a warp of the hot kernel serves a group of runs and
+//                        gathers one contiguous row per rating
 //   row_w_kernel         [1] for every user and item: W = own x Pw.  A lane owns a row, P sits in
 //                        shared memory and every read of it is a warp broadcast
 //                        (small_gemm_kernel: tiled fallback for row strides > 32 doubles)
@@ -23,7 +26,8 @@
 //                        streams its ratings; per rating it moves one neighbour row (8*NB bytes,
 //                        one 256-bit load per lane of a group of G lanes) and 4 bytes of index.
 //                        w comes from W via cp.async (prefetched one piece ahead), g overwrites W
-//                        in place.  Segments longer than MMSBM_PIECE_LEN ratings are cut into
+//                        in place.  Pieces are claimed from a launch-wide queue by persistent
+//                        CTAs (large problems) or from a per-CTA range of pieces (small ones).  Segments longer than MMSBM_PIECE_LEN ratings are cut into
 //                        pieces by the work schedule built with the index (graph_build.cu); their
 //                        partial g rows are added in piece order by segment_fixup_kernel
 //   row_n_kernel         [3] n_own = (G x Pn) o own / max(deg,1)   (normalisation fused)
@@ -471,7 +475,7 @@ static int env_int(const char* name, int dflt) {
 
 // NCH 32-byte chunks per row are spread over G lanes x CH chunks per lane with G <= 8 (three
 // shuffle levels per rating at most); UN steps in flight; MINB CTAs per SM the kernel is
-// compiled for.  Defaults from the sweep in profiles/ (more resident warps beat deeper unroll).
+// compiled for.  Defaults from the sweeps recorded in DESIGN.md section 5.
 static PassShape choose_shape(int NBp, double avg_degree) {
   const int NCH = NBp / 4;
   int CH = 8;
