@@ -1,22 +1,26 @@
-// The hot kernel of the EM iteration: one warp per segment (a user in the by-user pass, an
-// item in the by-item pass) streams the segment's ratings.  See em_step.cu for the algebra.
+// The hot kernel of the EM iteration: a warp takes one piece (up to MMSBM_PIECE_LEN ratings) of a
+// segment -- a user in the by-user pass, an item in the by-item pass -- and streams its ratings
+// level by level.  See em_step.cu for the algebra.
 //
-// Lane mapping (all compile time): groups of G lanes own one rating each, RPS = 32/G ratings
-// per step, UN steps in flight (SLOTS = UN*RPS ratings per chunk of work).  Lane q of a group
-// holds CH 32-byte chunks of the gathered neighbour row (chunk c*G+q), fetched with ONE 256-bit
-// read-only load per chunk (LDG.E.ENL2.256) -- a group covers a whole row in one instruction,
-// so the L1 sees ~1.6 wavefronts per rating instead of 10 for a lane-per-row layout
-// (profiles/r1_gather_microbench_*.txt).
+// Lane mapping (all compile time): G lanes hold one neighbour row, lane q its 32-byte chunks
+// c*G+q (CH of them), each fetched with ONE 256-bit read-only load (LDG.E.ENL2.256).  A warp
+// serves RUNS runs at once over rows interleaved in memory ([group][id][RUNS][NBp]), so a rating
+// occupies GR = G*RUNS lanes and its gather is one contiguous RUNS*8*NBp-byte read; RPS = 32/GR
+// ratings per step, UN steps per chunk of work (SLOTS = UN*RPS ratings).
 //
-//   S_n   = <w_level, row>      4*CH DFMA per lane + an all-reduce over the G lanes
-//   1/S_n                       MUFU.RCP64H + two Newton steps
+//   S_n   = <w_level, row>      4*CH DFMA per lane + a sum over the G lanes (5 lanes, 3 steps:
+//                               one reduce-scatter for the three dots of a chunk, GroupSum::sum3)
+//   1/S_n                       MUFU.RCP64H + one third-order correction
 //   g    += row / S_n           4*CH DFMA per lane, registers
-//   g_level -> global           once per (segment, level): sum over the RPS groups by shuffles
+//   g_level -> global           once per (piece, level): sum over the RPS groups by shuffles
 //
-// w comes from the W table (small_gemm_kernel) through cp.async, prefetched one segment ahead
-// into a double-buffered shared-memory row; g overwrites W in place.  Ratings are stored
-// grouped by level and chunks never straddle a level boundary, so the level -- hence w -- is
-// warp-uniform inside a chunk.
+// A chunk is computed in phases -- all UN loads, all dots, all reciprocals, all accumulations --
+// so that the loads issue back to back; the last chunk of a level is specialised on the number
+// of steps that hold ratings.  w comes from the W table (row_w_kernel) through cp.async into
+// shared memory (double buffered, the next piece's rows land while this piece runs; single
+// buffered for six runs); g overwrites W in place.  Ratings are stored grouped by level and
+// chunks never straddle a level boundary, so the level -- hence w -- is warp-uniform in a chunk.
+// Pieces are claimed with an atomic counter: launch-wide (persistent CTAs) or per CTA.
 #pragma once
 #include <type_traits>
 
@@ -190,10 +194,10 @@ segment_pass_kernel(const SegArgs A) {
   __syncthreads();
 
   const int grp = lane / GR, lig = lane - grp * GR;
-  const int rsel = lig / G, q = lig - rsel * G;  // which run of the pair, which lane of the group
+  const int rsel = lig / G, q = lig - rsel * G;  // which run of the group of runs, which lane of the row
   const bool lane_on = grp < RPS;                // lanes past RPS*GR idle (32 % GR of them)
   const int run0 = A.run_base + blockIdx.y * RUNS, run = run0 + rsel;
-  // this CTA's range of pieces (a piece = up to MMSBM_PIECE_LEN ratings of one segment)
+  // the work schedule (a piece = up to MMSBM_PIECE_LEN ratings of one segment)
   const int32_t* piece_seg = A.sched + 4;
   const int32_t* piece_idx = piece_seg + A.pmax;
   const int32_t* piece_slot = piece_idx + A.pmax;
