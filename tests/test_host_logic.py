@@ -215,3 +215,23 @@ def test_encoding_threaded_hash_passes_match_serial():
     np.testing.assert_array_equal(slow.parse_train_data(slow._to_object_str(df.iloc[:20000].copy())),
                                   DataHandler().format_train_data(df.iloc[:20000]))
     assert out.shape == (n, 3) and out[:, 0].max() == len(fast.obs_dict) - 1
+
+
+@pytest.mark.parametrize("backend", ["numba", "numpy"])
+def test_bench_reference_arm_runs_without_a_gpu(backend):
+    """`bench.py --impl reference` is the CPU arm of the bench contract: one JSON line, the same
+    metric / unit / config keys as the GPU arm, impl = reference, no device work."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "ml100k",
+                          "--cpu-rows", "3000", "--steps", "1", "--warmup", "1", "--cpu-backend", backend],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "rating-updates/sec" and line["value"] > 0
+    assert line["unit"] == "rating-updates/s" and line["higher_is_better"] is True
+    assert line["config"]["workload"] == "ml100k" and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["backend"] == backend
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
