@@ -484,8 +484,8 @@ static PassShape choose_shape(int NBp, double avg_degree) {
   }
   const int G = (NCH + CH - 1) / CH;
   PassShape sh{G, CH, 1, 1};   // CH == 1 implies NBp == 4*G (the kernel relies on it)
-  // three row loads in flight per warp (a fourth is not issued back to back by ptxas: the
-  // warp's scoreboards are taken), 3 CTAs/SM: best of the UN x MINB sweep on both passes
+  // three row loads in flight per warp, 3 CTAs/SM: best of the UN x MINB sweep on both passes
+  // (four loads spill at 80 registers, 128 registers cost a third of the resident warps)
   (void)avg_degree;
   if (CH == 1) { sh.UN = (G == 1) ? 1 : (G == 2) ? 2 : 3; sh.MINB = 3; }   // UN * (32 / G) <= 32
   else if (CH == 2) { sh.UN = 1; sh.MINB = 3; }
