@@ -235,3 +235,16 @@ def test_bench_reference_arm_runs_without_a_gpu(backend):
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["backend"] == backend
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0,
                            "d2h_bytes_per_step": 0}
+
+
+def test_bench_algorithmic_bytes_match_the_survey_table():
+    """bench.b_alg is SURVEY.md section 8d's B_alg = 8(K+L) + 16/S + 16(K U + L I)/N; the table there
+    lists 180.2 / 163.6 / 324.6 / 530.5 bytes per rating-update for the four shapes."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    want = {"ml100k": 180.2, "ml1m": 163.6, "ml20m": 324.6, "netflix": 530.5}
+    for name, (U, I, N, K, L, S) in bench.WORKLOADS.items():
+        assert abs(bench.b_alg(U, I, N, K, L, S) - want[name]) < 0.06, name
