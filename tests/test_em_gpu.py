@@ -534,6 +534,7 @@ def test_reference_loader_contract():
 @pytest.mark.parametrize("shape", [
     dict(name="ML-1M", N=1_000_000, U=6040, I=3706, K=10, L=10, S=8),
     dict(name="ML-20M", N=20_000_000, U=138_000, I=27_000, K=20, L=20, S=2),
+    dict(name="ML-20M six runs per warp + a single", N=20_000_000, U=138_000, I=27_000, K=20, L=20, S=7),
 ])
 def test_full_size_invariants(shape):
     """At sizes the oracle cannot reach, check what must hold for any input: each rating
