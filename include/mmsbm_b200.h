@@ -50,7 +50,7 @@
 extern "C" {
 #endif
 
-#define MMSBM_ABI_VERSION 3
+#define MMSBM_ABI_VERSION 4
 
 /* a warp of the hot kernel processes at most this many ratings of one segment at a time; longer
  * segments are cut into pieces whose partial sums are added in piece order (see usched/isched) */
@@ -96,6 +96,15 @@ int mmsbm_graph_build(const int32_t* user_dev, const int32_t* item_dev, const in
                       int32_t* usched_dev, int32_t* isched_dev,
                       void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* one side only: segments = `id_dev` (already shifted to start at 0, < n_ids), neighbour ids kept as
+ * given.  A rank of a sharded run builds its CSR from the ratings of its own users and its CSC from
+ * the ratings of its own items with two such calls (workspace: mmsbm_graph_workspace_bytes with
+ * n_users = n_items = n_ids; sched: mmsbm_sched_elems(n_ratings, n_ids)) */
+int mmsbm_graph_build_side(const int32_t* id_dev, const int32_t* other_dev, const int32_t* level_dev,
+                           int64_t n_ratings, int32_t n_ids, int32_t n_levels,
+                           int32_t* seg_dev, int32_t* adj_dev, int32_t* perm_dev, int32_t* deg_dev,
+                           int32_t* sched_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* ---- a2+a3+a4: one EM iteration for S runs, replaces update_coefficients
  *      (src/kernels_numpy.py:43-79) + normalize_with_d x2 + normalize_with_self
  *      (src/expectation_maximization.py:118-155), i.e. the loop body src/mmsbm.py:244-250 --- */
@@ -136,6 +145,57 @@ int mmsbm_em_run(const int32_t* useg_dev, const int32_t* uadj_dev, const int32_t
  * pr normalised over the rating axis (zero sums divide by one). In place. */
 int mmsbm_em_finalize(double* eta_dev, const int32_t* ideg_dev, int32_t n_items, int32_t L,
                       double* pr_dev, int32_t K, int32_t n_levels, int32_t n_runs, void* stream);
+
+/* ---- a9 / e3: ONE set of S runs sharded over the GPUs of a box, one process per GPU; replaces the
+ *      process pool of src/mmsbm.py:182-185 for a fit too slow or too large for one GPU.
+ *      Rank g owns a contiguous user range and a contiguous item range (both balanced by rating
+ *      count): a CSR over its users built from all their ratings, a CSC over its items built from
+ *      all theirs (mmsbm_graph_build_side), and the theta / eta rows of those ids.  n_theta / n_eta
+ *      of owned ids are complete local sums.  The rows a pass gathers live in an EXCHANGE BUFFER
+ *      (mmsbm_shard_exchange_bytes; allocate it with mmsbm_ipc_alloc, map the peers' with
+ *      mmsbm_ipc_open) that every rank fills for every other rank by copy-engine DMA over NVLink
+ *      while the segment pass computes.  The only collective per iteration is one ncclAllReduce of
+ *      n_pr [S][K][L][R], which doubles as the barrier of the exchange.  See csrc/sharded_run.cu. */
+typedef struct mmsbm_shard_t {
+  const int32_t *useg_dev, *uadj_dev, *udeg_dev, *usched_dev;  /* CSR over the own users (ids shifted by user_lo;
+                                                                   uadj holds GLOBAL item ids)               */
+  int64_t n_ratings_u;                                         /* ratings of the own users                  */
+  const int32_t *iseg_dev, *iadj_dev, *ideg_dev, *isched_dev;  /* CSC over the own items (iadj: global users) */
+  int64_t n_ratings_i;
+  int32_t n_users_own, user_lo, n_items_own, item_lo;          /* own ranges [lo, lo + n_own)               */
+  int32_t n_users, n_items, n_levels, K, L, n_runs;            /* global sizes                              */
+  int32_t rank, world;
+  void* const* exchange_dev;   /* [world] base of every rank's exchange buffer as mapped HERE (own one included) */
+  void* nccl_comm;             /* ncclComm_t over the world ranks, opaque (NULL when world == 1); any communicator
+                                  created by the caller works, e.g. mmsbm_nccl_comm_init or torch's              */
+} mmsbm_shard_t;
+
+/* NCCL is bound at run time from the library the host process already uses (path NULL: "libnccl.so.2") */
+int mmsbm_nccl_load(const char* libnccl_path);
+int mmsbm_nccl_unique_id(unsigned char* id128);                      /* rank 0, then broadcast by the caller */
+int mmsbm_nccl_comm_init(const unsigned char* id128, int32_t rank, int32_t world, void** comm_out);
+int mmsbm_nccl_comm_destroy(void* comm);
+/* device memory other processes of the box can map (cudaMalloc + CUDA IPC) */
+int mmsbm_ipc_alloc(size_t bytes, void** dev_ptr_out, unsigned char* handle64_out);
+int mmsbm_ipc_open(const unsigned char* handle64, void** dev_ptr_out);
+int mmsbm_ipc_close(void* dev_ptr);
+int mmsbm_ipc_free(void* dev_ptr);
+
+int mmsbm_shard_exchange_bytes(int32_t n_users, int32_t n_items, int32_t K, int32_t L, int32_t n_runs,
+                               size_t* bytes);
+int mmsbm_shard_workspace_bytes(const mmsbm_shard_t* shard, size_t* bytes);
+/* gather tables of half `half` (0/1) of every rank's exchange buffer <- this rank's own rows
+ * (theta_own [S][n_users_own][ldk], eta_own [S][n_items_own][ldl]); collective: every rank calls it */
+int mmsbm_shard_publish(const mmsbm_shard_t* shard, const double* theta_own_dev, const double* eta_own_dev,
+                        int32_t half, void* stream);
+/* `iterations` steps; own rows ping-pong between _a and _b like mmsbm_em_run, pr [S][K][L][R] is
+ * replicated.  Precondition: half `half` holds the parameters of the _a buffers on every rank.
+ * prof (optional, float[2]): mean device ms per iteration, mean ms of it spent waiting for the
+ * exchange and the n_pr all-reduce; measuring synchronises every iteration. */
+int mmsbm_em_run_sharded(const mmsbm_shard_t* shard, int32_t iterations,
+                         double* theta_own_a_dev, double* eta_own_a_dev, double* pr_a_dev,
+                         double* theta_own_b_dev, double* eta_own_b_dev, double* pr_b_dev,
+                         int32_t half, void* workspace_dev, size_t workspace_bytes, void* stream, float* prof);
 
 /* ---- a5: the reference's "likelihood", replaces ExpectationMaximization.compute_likelihood
  *      (src/expectation_maximization.py:157-167); out_dev[S] ------------------------------ */

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmmsbm_b200.so")
 SOURCES = ["em_step.cu", "seg_inst_ch1.cu", "seg_inst_ch2.cu", "seg_inst_ch4.cu", "seg_inst_pair.cu", "seg_inst_hexa.cu", "graph_build.cu",
-           "reductions.cu", "host_api.cu"]
+           "reductions.cu", "host_api.cu", "sharded_run.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall", "-DMMSBM_B200",   # no --use_fast_math: IEEE fp64 throughout
@@ -39,7 +39,7 @@ def build_library(force=False, verbose=False, check=False):
     nvcc = _nvcc()
     suffix, extra, lib = ("_chk.o", ["-DMMSBM_BOUNDS_CHECK"], LIB.replace(".so", "_check.so")) if check \
         else (".o", ["-DNDEBUG"], LIB)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "segment_pass.cuh"),
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "segment_pass.cuh"), os.path.join(CSRC, "em_internal.cuh"),
                os.path.join(HERE, "..", "include", "mmsbm_b200.h"), os.path.abspath(__file__)]
     objs, jobs = [], []
     for src in SOURCES:
@@ -57,7 +57,7 @@ def build_library(force=False, verbose=False, check=False):
                 if res.returncode:
                     raise RuntimeError("nvcc failed for " + cmd[-3])
     if jobs or force or _stale(lib, objs):
-        cmd = [nvcc, "-shared", "-o", lib] + objs + ["-lcudart"]
+        cmd = [nvcc, "-shared", "-o", lib] + objs + ["-lcudart", "-ldl"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode:
             sys.stderr.write(res.stdout + res.stderr)

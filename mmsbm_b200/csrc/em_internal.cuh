@@ -1,0 +1,44 @@
+// Launch helpers of the EM iteration shared by em_step.cu (one GPU) and sharded_run.cu (the
+// user-range x item-range sharded loop).  Kernels and their documentation live in em_step.cu.
+#pragma once
+#include "common.cuh"
+#include "segment_pass.cuh"
+
+namespace mmsbm {
+
+constexpr int kPrSlabs = 128;
+
+int env_int(const char* name, int dflt);
+int sm_count();                       // multiprocessors of the current device (cached per device)
+
+// How the S runs of a launch row are served by the segment pass for neighbour rows of NBp
+// doubles: runs [0, 6*hexas) six per warp, then `pairs` pairs (pair groups numbered over ALL
+// runs, first one = pair_group0), the rest one run per warp from run `single_from`.
+struct RunPlan { int hexas, pairs, pair_group0, single_from; };
+RunPlan plan_runs(int NBp, int n_runs, bool hexa_table);
+
+int launch_prep_p(const double* pr, int K, int L, int R, int ldk, int ldl, int n_runs, double* pw_u,
+                  double* pn_u, double* pw_i, double* pn_i, cudaStream_t st);
+
+// dst[(grp*n_dst + row0 + id)*gs + j][ld] <- src[(gs*grp + j)*n_src + id][ld] for grp in
+// [group0, group0+groups), id < n_src: the rows of run groups side by side, written into a table
+// of n_dst rows per group starting at row row0 (gs == 1: a plain copy of run `grp`)
+int launch_interleave(const double* src, double* dst, int n_src, int n_dst, int row0, int ld,
+                      int group0, int groups, int gs, cudaStream_t st);
+
+int launch_w(const double* own, const double* pw, double* W, int M, int LD, int RNB, int n_runs,
+             cudaStream_t st);
+int launch_n(const double* G, const double* pn, const double* own, const int32_t* deg, double* out,
+             int M, int LD, int RNB, int normalize, int n_runs, cudaStream_t st);
+
+int launch_segment_pass_and_fixup(SegArgs a, const double* nbr_pairs, const double* nbr_hexa,
+                                  int64_t n_ratings, int n_runs, cudaStream_t st);
+
+// n_pr from the side whose segments carry the accumulation: Acc = sum_seg own (x) g over `nseg`
+// segments (kPrSlabs partial sums, fixed order), x P, optionally normalised over the rating axis
+int launch_pr(const double* own, const double* g, double* partial, const double* pr, double* pr_out,
+              int nseg, int NA, int lda, int NBp, int K, int L, int R, int n_runs, bool transposed,
+              bool normalize, cudaStream_t st);
+int launch_finalize_pr(double* pr, int kl_total, int R, cudaStream_t st);
+
+}  // namespace mmsbm

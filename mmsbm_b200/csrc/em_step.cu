@@ -37,11 +37,11 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "em_internal.cuh"
 #include "segment_pass.cuh"
 
 namespace mmsbm {
 
-constexpr int kPrSlabs = 128;
 constexpr int kPrThreads = 128;
 constexpr int kPrBatch = 16;    // segments staged per smem batch
 constexpr int kGemmThreads = 256;
@@ -67,20 +67,22 @@ __global__ void __launch_bounds__(128) segment_fixup_kernel(const SegArgs A) {
   }
 }
 
-// ---- rows of run groups interleaved: dst[grp][id][j][ld] <- src[gs*grp + j][id][ld], j < gs ------
-__global__ void interleave_runs_kernel(const double* __restrict__ src, double* __restrict__ dst, int n,
-                                       int ld, int groups, int gs) {
+// ---- rows of run groups interleaved: dst[grp][row0 + id][j][ld] <- src[gs*grp + j][id][ld], j < gs,
+//      for the groups [group0, group0 + groups); src holds n_src rows per run, dst n_dst rows per
+//      group (n_dst > n_src when a rank fills its slice of a table that spans all ranks) ------
+__global__ void interleave_runs_kernel(const double* __restrict__ src, double* __restrict__ dst, int n_src,
+                                       int n_dst, int row0, int ld, int group0, int groups, int gs) {
   const int c4 = ld >> 2;
-  const size_t total = (size_t)groups * n * gs * c4;
+  const size_t total = (size_t)groups * n_src * gs * c4;
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int c = (int)(t % c4);
   const int j = (int)((t / c4) % gs);
   const size_t rest = t / c4 / gs;
-  const int id = (int)(rest % n);
-  const size_t p = rest / n;
-  const double4_t v = ldg256(src + (((size_t)(gs * p + j) * n + id) * ld + 4 * c));
-  stg256(dst + 4 * t, v);
+  const int id = (int)(rest % n_src);
+  const size_t p = group0 + rest / n_src;
+  const double4_t v = ldg256(src + (((size_t)(gs * p + j) * n_src + id) * ld + 4 * c));
+  stg256(dst + (((p * n_dst + row0 + id) * gs + j) * ld + 4 * c), v);
 }
 
 // ---- P in operand layout -------------------------------------------------------------------
@@ -468,9 +470,22 @@ __global__ void finalize_pr_kernel(double* pr, int KL_total, int R) {
 // ------------------------------------------------------------------------------------------
 struct PassShape { int G, CH, UN, MINB; };
 
-static int env_int(const char* name, int dflt) {
+int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
+}
+
+// multiprocessors of the current device (148 on a B200), cached per device ordinal
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
 }
 
 // NCH 32-byte chunks per row are spread over G lanes x CH chunks per lane with G <= 8 (three
@@ -502,7 +517,7 @@ static int segs_per_cta_for(int64_t pmax, int64_t n_ratings, int grid_y) {
   if (e > 0) return e;
   const double avg_piece = (double)(n_ratings > 0 ? n_ratings : 1) / (double)(pmax > 0 ? pmax : 1);
   int64_t spc = ((int64_t)(6144.0 / (avg_piece > 1.0 ? avg_piece : 1.0)) + kWarps / 2) / kWarps * kWarps;
-  const int64_t fill = pmax * grid_y / (148 * 3 * 6) / kWarps * kWarps;
+  const int64_t fill = pmax * grid_y / (sm_count() * 3 * 6) / kWarps * kWarps;
   if (spc > fill) spc = fill;
   if (spc < kWarps) spc = kWarps;               // one piece per warp at least
   if (spc > 64) spc = 64;
@@ -519,7 +534,7 @@ static bool pairs_enabled(int NBp, int n_runs) {
 // many as stay resident (148 SMs x CTAs per SM), one starting piece per warp at least.
 static unsigned grid_x_for(const SegArgs& a, int ctas_per_sm) {
   if (!a.counters) return (unsigned)((a.pmax + a.segs_per_cta - 1) / a.segs_per_cta);
-  const int64_t want = (a.pmax + kWarps - 1) / kWarps, resident = (int64_t)148 * ctas_per_sm;
+  const int64_t want = (a.pmax + kWarps - 1) / kWarps, resident = (int64_t)sm_count() * ctas_per_sm;
   return (unsigned)(want < resident ? want : resident);
 }
 
@@ -528,14 +543,27 @@ static bool hexa_enabled(int NBp, int n_runs) {
   return n_runs >= 6 && NBp == 20 && env_int("MMSBM_HEXA", 1) != 0;
 }
 
+RunPlan plan_runs(int NBp, int n_runs, bool hexa_table) {
+  RunPlan p{0, 0, 0, 0};
+  if (hexa_table && hexa_enabled(NBp, n_runs)) p.hexas = n_runs / 6;
+  p.single_from = 6 * p.hexas;
+  if (pairs_enabled(NBp, n_runs - p.single_from)) {
+    p.pairs = (n_runs - p.single_from) / 2;
+    p.pair_group0 = p.single_from / 2;            // pairs are numbered over all runs (6 | single_from)
+    p.single_from += 2 * p.pairs;
+  }
+  return p;
+}
+
 static int launch_segment_pass_impl(SegArgs a, const double* nbr_pairs, const double* nbr_hexa,
                                     int64_t n_ratings, int n_runs, cudaStream_t st) {
   const double avg_degree = (double)n_ratings / (double)a.nseg;
   PassShape sh = choose_shape(a.NBp, avg_degree);
   const int un_e = env_int("MMSBM_UN", 0), occ_e = env_int("MMSBM_OCC", 0);
-  int single_from = 0;                           // runs [single_from, n_runs) go one run per warp
-  if (nbr_hexa && hexa_enabled(a.NBp, n_runs)) {
-    const int hexas = n_runs / 6;
+  const RunPlan plan = plan_runs(a.NBp, n_runs, nbr_hexa != nullptr);
+  const int single_from = plan.single_from;      // runs [single_from, n_runs) go one run per warp
+  if (plan.hexas > 0) {
+    const int hexas = plan.hexas;
     SegArgs p = a;
     p.nbr = nbr_hexa;
     p.run_base = 0;
@@ -553,15 +581,15 @@ static int launch_segment_pass_impl(SegArgs a, const double* nbr_pairs, const do
       if (rc == MMSBM_ERANGE) set_error("no six-run segment-pass variant for G=%d", sh.G);
       return rc;
     }
-    single_from = 6 * hexas;
-    if (single_from == n_runs) return 0;
+    if (single_from == n_runs && plan.pairs == 0) return 0;
   }
-  if (nbr_pairs && pairs_enabled(a.NBp, n_runs - single_from)) {
-    const int pairs = (n_runs - single_from) / 2;
+  if (plan.pairs > 0) {
+    MMSBM_REQUIRE(nbr_pairs, MMSBM_EINVAL, "segment pass: the table of run pairs is missing");
+    const int pairs = plan.pairs;
     SegArgs p = a;
     p.nbr = nbr_pairs;
-    p.run_base = single_from;
-    p.grp_base = single_from / 2;                // pairs are numbered over all runs (6 | single_from)
+    p.run_base = 6 * plan.hexas;
+    p.grp_base = plan.pair_group0;
     p.counters = a.counters;
     p.segs_per_cta = segs_per_cta_for(a.pmax, n_ratings, pairs);
     const unsigned gx = grid_x_for(p, occ_e > 0 ? occ_e : 3);
@@ -578,9 +606,8 @@ static int launch_segment_pass_impl(SegArgs a, const double* nbr_pairs, const do
       if (rc == MMSBM_ERANGE) set_error("no paired segment-pass variant for G=%d", sh.G);
       return rc;
     }
-    single_from += 2 * pairs;
-    if (single_from == n_runs) return 0;
   }
+  if (single_from == n_runs) return 0;
   a.run_base = single_from;
   a.segs_per_cta = segs_per_cta_for(a.pmax, n_ratings, n_runs - single_from);
   const unsigned gx = grid_x_for(a, occ_e > 0 ? occ_e : sh.MINB);
@@ -609,11 +636,12 @@ static int launch_segment_pass_impl(SegArgs a, const double* nbr_pairs, const do
   return rc;
 }
 
-static int launch_segment_pass_and_fixup(SegArgs a, const double* nbr_pairs, const double* nbr_hexa,
-                                         int64_t n_ratings, int n_runs, cudaStream_t st) {
+int launch_segment_pass_and_fixup(SegArgs a, const double* nbr_pairs, const double* nbr_hexa,
+                                  int64_t n_ratings, int n_runs, cudaStream_t st) {
   int rc = launch_segment_pass_impl(a, nbr_pairs, nbr_hexa, n_ratings, n_runs, st);
   if (rc) return rc;
-  const unsigned gx = (unsigned)(a.lmax < 592 ? a.lmax : 592);
+  const int64_t fix_ctas = 4 * sm_count();
+  const unsigned gx = (unsigned)(a.lmax < fix_ctas ? a.lmax : fix_ctas);
   segment_fixup_kernel<<<dim3(gx, n_runs), 128, 0, st>>>(a);
   MMSBM_LAUNCH_CHECK("segment_fixup_kernel");
   return 0;
@@ -636,7 +664,7 @@ static int launch_gemm(GemmArgs g, int n_runs, cudaStream_t st) {
   auto kern = small_gemm_kernel<EPI>;
   MMSBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_tiles = (g.M + BM - 1) / BM;
-  int per_run = (148 * 3 + n_runs - 1) / n_runs;      // ~3 persistent CTAs per SM in total
+  int per_run = (sm_count() * 3 + n_runs - 1) / n_runs;      // ~3 persistent CTAs per SM in total
   if (per_run > n_tiles) per_run = n_tiles;
   if (per_run < 1) per_run = 1;
   kern<<<dim3(per_run, n_runs), kGemmThreads, smem, st>>>(g);
@@ -645,8 +673,8 @@ static int launch_gemm(GemmArgs g, int n_runs, cudaStream_t st) {
 }
 
 // dispatch of the two contractions: lane-per-row kernels for row strides <= 32, tiled GEMM beyond
-static int launch_w(const double* own, const double* pw, double* W, int M, int LD, int RNB, int n_runs,
-                    cudaStream_t st) {
+int launch_w(const double* own, const double* pw, double* W, int M, int LD, int RNB, int n_runs,
+             cudaStream_t st) {
   const size_t smem = (size_t)LD * RNB * 8;
   const int rows_env = env_int("MMSBM_ROWS", 2);
 #define MMSBM_ROW_W(LDv)                                                                        \
@@ -655,7 +683,7 @@ static int launch_w(const double* own, const double* pw, double* W, int M, int L
     const bool two = kRows == 2 && rows_env == 2;                                               \
     auto kern = two ? row_w_kernel<LDv, kRows> : row_w_kernel<LDv, 1>;                          \
     const int per = kRowThreads * (two ? 2 : 1);                                                \
-    const int gx = min((M + per - 1) / per, 148 * 2);                                           \
+    const int gx = min((M + per - 1) / per, sm_count() * 2);                                           \
     MMSBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<dim3(gx, n_runs), kRowThreads, smem, st>>>(own, pw, W, M, RNB);                      \
     MMSBM_LAUNCH_CHECK("row_w_kernel");                                                         \
@@ -668,8 +696,8 @@ static int launch_w(const double* own, const double* pw, double* W, int M, int L
   return launch_gemm<false>(g, n_runs, st);
 }
 
-static int launch_n(const double* G, const double* pn, const double* own, const int32_t* deg, double* out,
-                    int M, int LD, int RNB, int normalize, int n_runs, cudaStream_t st) {
+int launch_n(const double* G, const double* pn, const double* own, const int32_t* deg, double* out,
+             int M, int LD, int RNB, int normalize, int n_runs, cudaStream_t st) {
   const size_t smem = (size_t)LD * RNB * 8;
   // one row per lane here: two rows cost occupancy (142 registers) and measured slower
   const int rows_env = env_int("MMSBM_ROWS_N", 1);
@@ -679,7 +707,7 @@ static int launch_n(const double* G, const double* pn, const double* own, const 
     const bool two = kRows == 2 && rows_env == 2;                                               \
     auto kern = two ? row_n_kernel<LDv, kRows> : row_n_kernel<LDv, 1>;                          \
     const int per = kRowThreads * (two ? 2 : 1);                                                \
-    const int gx = min((M + per - 1) / per, 148 * 2);                                           \
+    const int gx = min((M + per - 1) / per, sm_count() * 2);                                           \
     MMSBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<dim3(gx, n_runs), kRowThreads, smem, st>>>(G, pn, own, deg, out, M, RNB, normalize); \
     MMSBM_LAUNCH_CHECK("row_n_kernel");                                                         \
@@ -690,6 +718,53 @@ static int launch_n(const double* G, const double* pn, const double* own, const 
 #undef MMSBM_ROW_N
   GemmArgs g{G, pn, out, own, deg, M, LD, RNB, RNB, 0, normalize, 0};
   return launch_gemm<true>(g, n_runs, st);
+}
+
+int launch_prep_p(const double* pr, int K, int L, int R, int ldk, int ldl, int n_runs, double* pw_u,
+                  double* pn_u, double* pw_i, double* pn_i, cudaStream_t st) {
+  const int total = ldk * ldl * R;
+  prep_p_kernel<<<dim3((total + 255) / 256, n_runs), 256, 0, st>>>(pr, K, L, R, ldk, ldl, pw_u, pn_u, pw_i, pn_i);
+  MMSBM_LAUNCH_CHECK("prep_p_kernel");
+  return 0;
+}
+
+int launch_interleave(const double* src, double* dst, int n_src, int n_dst, int row0, int ld, int group0,
+                      int groups, int gs, cudaStream_t st) {
+  const size_t tot = (size_t)groups * n_src * gs * (ld / 4);
+  if (tot == 0) return 0;
+  interleave_runs_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, dst, n_src, n_dst, row0, ld,
+                                                                        group0, groups, gs);
+  MMSBM_LAUNCH_CHECK("interleave_runs_kernel");
+  return 0;
+}
+
+int launch_pr(const double* own, const double* g, double* partial, const double* pr, double* pr_out,
+              int nseg, int NA, int lda, int NBp, int K, int L, int R, int n_runs, bool transposed,
+              bool normalize, cudaStream_t st) {
+  PrArgs pa{};
+  pa.own = own; pa.g = g; pa.partial = partial;
+  pa.nseg = nseg; pa.NA = NA; pa.lda = lda; pa.RNB = R * NBp;
+  const size_t smem = (size_t)kPrBatch * (pa.lda + pa.RNB) * 8;
+  MMSBM_CUDA(cudaFuncSetAttribute(pr_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+  pr_accumulate_kernel<<<dim3(kPrSlabs, n_runs), kPrThreads, smem, st>>>(pa);
+  MMSBM_LAUNCH_CHECK("pr_accumulate_kernel");
+  PrFinArgs fa{};
+  fa.partial = partial; fa.pr = pr; fa.pr_out = pr_out;
+  fa.K = K; fa.L = L; fa.R = R; fa.NA = NA; fa.NBp = NBp;
+  fa.transposed = transposed ? 1 : 0;
+  fa.normalize = normalize ? 1 : 0;
+  const size_t fin_smem = (size_t)(kFinWarps + 1) * R * NBp * 8;
+  MMSBM_CUDA(cudaFuncSetAttribute(pr_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+  pr_finalize_kernel<<<dim3(NA, n_runs), kFinWarps * 32, fin_smem, st>>>(fa);
+  MMSBM_LAUNCH_CHECK("pr_finalize_kernel");
+  return 0;
+}
+
+int launch_finalize_pr(double* pr, int kl_total, int R, cudaStream_t st) {
+  finalize_pr_kernel<<<(kl_total + 127) / 128, 128, 0, st>>>(pr, kl_total, R);
+  MMSBM_LAUNCH_CHECK("finalize_pr_kernel");
+  return 0;
 }
 
 struct EmDims {
@@ -800,26 +875,14 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
 #define MMSBM_SIDE_DONE(k) do { if (ov) MMSBM_CUDA(cudaEventRecord(ov->e[k], s2)); } while (0)
   // ---- P tables and w = own x Pw for every user and item ----
   {
-    const int total = d.ldk * d.ldl * R;
     if (dyn) MMSBM_CUDA(cudaMemsetAsync(counters, 0, d.ctr_elems * 4, st));   // piece queues of both passes
-    prep_p_kernel<<<dim3((total + 255) / 256, S), 256, 0, st>>>(pr, K, L, R, d.ldk, d.ldl, pw_u, pn_u, pw_i, pn_i);
-    MMSBM_LAUNCH_CHECK("prep_p_kernel");
+    if ((rc = launch_prep_p(pr, K, L, R, d.ldk, d.ldl, S, pw_u, pn_u, pw_i, pn_i, st))) return rc;
     MMSBM_FORK(0);                                                  // side: after the P tables
-    if (hexa_enabled(d.ldl, S)) {      // eta rows of six runs side by side (by-user pass gathers)
-      const size_t tot = (size_t)(S / 6) * I * 6 * (d.ldl / 4);
-      interleave_runs_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(eta, et6, I, d.ldl, S / 6, 6);
-      MMSBM_LAUNCH_CHECK("interleave_runs_kernel");
-    }
-    if (pairs_enabled(d.ldl, S)) {     // eta rows of run pairs side by side
-      const size_t tot = (size_t)(S / 2) * I * 2 * (d.ldl / 4);
-      interleave_runs_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(eta, et2, I, d.ldl, S / 2, 2);
-      MMSBM_LAUNCH_CHECK("interleave_runs_kernel");
-    }
-    if (pairs_enabled(d.ldk, S)) {     // theta rows likewise (by-item pass gathers)
-      const size_t tot = (size_t)(S / 2) * U * 2 * (d.ldk / 4);
-      interleave_runs_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(theta, th2, U, d.ldk, S / 2, 2);
-      MMSBM_LAUNCH_CHECK("interleave_runs_kernel");
-    }
+    // rows of run groups side by side: eta for the by-user pass (six runs when rows hold 20
+    // doubles, pairs), theta for the by-item pass (pairs)
+    if (hexa_enabled(d.ldl, S) && (rc = launch_interleave(eta, et6, I, I, 0, d.ldl, 0, S / 6, 6, st))) return rc;
+    if (pairs_enabled(d.ldl, S) && (rc = launch_interleave(eta, et2, I, I, 0, d.ldl, 0, S / 2, 2, st))) return rc;
+    if (pairs_enabled(d.ldk, S) && (rc = launch_interleave(theta, th2, U, U, 0, d.ldk, 0, S / 2, 2, st))) return rc;
     if ((rc = launch_w(theta, pw_u, wg_u, U, d.ldk, d.rnb_u, S, st))) return rc;
     if ((rc = launch_w(eta, pw_i, wg_i, I, d.ldl, d.rnb_i, S, s2))) return rc;
     MMSBM_SIDE_DONE(1);                                             // w of the items ready
@@ -854,28 +917,10 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
   MMSBM_SIDE_DONE(5);
   MMSBM_MARK(5);
   // ---- pr' ----
-  PrArgs pa{};
-  pa.own = d.emit_items ? eta : theta;
-  pa.g = d.emit_items ? wg_i : wg_u;
-  pa.partial = partial;
-  pa.nseg = d.nseg_e; pa.NA = d.NA_e; pa.lda = d.emit_items ? d.ldl : d.ldk;
-  pa.RNB = R * d.NBp_e;
-  size_t smem = (size_t)kPrBatch * (pa.lda + pa.RNB) * 8;
-  MMSBM_CUDA(cudaFuncSetAttribute(pr_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-  pr_accumulate_kernel<<<dim3(kPrSlabs, S), kPrThreads, smem, st>>>(pa);
-  MMSBM_LAUNCH_CHECK("pr_accumulate_kernel");
+  if ((rc = launch_pr(d.emit_items ? eta : theta, d.emit_items ? wg_i : wg_u, partial, pr, pr_out, d.nseg_e,
+                      d.NA_e, d.emit_items ? d.ldl : d.ldk, d.NBp_e, K, L, R, S, d.emit_items,
+                      (flags & MMSBM_RAW_ETA_PR) == 0, st))) return rc;
   MMSBM_MARK(6);
-
-  PrFinArgs fa{};
-  fa.partial = partial; fa.pr = pr; fa.pr_out = pr_out;
-  fa.K = K; fa.L = L; fa.R = R; fa.NA = d.NA_e; fa.NBp = d.NBp_e;
-  fa.transposed = d.emit_items ? 1 : 0;
-  fa.normalize = (flags & MMSBM_RAW_ETA_PR) ? 0 : 1;
-  const size_t fin_smem = (size_t)(kFinWarps + 1) * R * d.NBp_e * 8;
-  MMSBM_CUDA(cudaFuncSetAttribute(pr_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-  pr_finalize_kernel<<<dim3(d.NA_e, S), kFinWarps * 32, fin_smem, st>>>(fa);
-  MMSBM_LAUNCH_CHECK("pr_finalize_kernel");
   MMSBM_MARK(7);
   if (ov) {                                                         // join: theta' and eta' are ready
     MMSBM_CUDA(cudaStreamWaitEvent(st, ov->e[4], 0));
@@ -1002,8 +1047,5 @@ extern "C" int mmsbm_em_finalize(double* eta, const int32_t* ideg, int32_t I, in
   size_t total = (size_t)S * I * ldl;
   finalize_eta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(eta, ideg, I, ldl, L, total);
   MMSBM_LAUNCH_CHECK("finalize_eta_kernel");
-  int kl = S * K * L;
-  finalize_pr_kernel<<<(kl + 127) / 128, 128, 0, st>>>(pr, kl, R);
-  MMSBM_LAUNCH_CHECK("finalize_pr_kernel");
-  return 0;
+  return launch_finalize_pr(pr, S * K * L, R, st);
 }

@@ -396,3 +396,25 @@ extern "C" int mmsbm_graph_build(const int32_t* user, const int32_t* item, const
   if ((rc = build_one(item, user, level, N, I, R, iseg, iadj, iperm, ideg, w, st))) return rc;
   return build_schedule(ideg, I, N, isched, w, st);
 }
+
+// One side only (a rank of a sharded run holds a CSR over its own users built from their ratings
+// and a CSC over its own items built from theirs -- two different row sets): `id` selects the
+// segment (already shifted to start at 0), `other` is the neighbour id kept in adj (global).
+extern "C" int mmsbm_graph_build_side(const int32_t* id, const int32_t* other, const int32_t* level,
+                                      int64_t N, int32_t n_ids, int32_t R, int32_t* seg, int32_t* adj,
+                                      int32_t* perm, int32_t* deg, int32_t* sched, void* ws,
+                                      size_t ws_bytes, void* stream) {
+  MMSBM_REQUIRE(seg && deg && sched && ws, MMSBM_EINVAL, "mmsbm_graph_build_side: null pointer");
+  MMSBM_REQUIRE(N == 0 || (id && other && level && adj && perm), MMSBM_EINVAL,
+                "mmsbm_graph_build_side: null pointer");
+  size_t need = 0;
+  int rc = mmsbm_graph_workspace_bytes(N, n_ids, n_ids, R, &need);
+  if (rc) return rc;
+  MMSBM_REQUIRE(ws_bytes >= need, MMSBM_ENOMEM, "mmsbm_graph_build_side: workspace %zu < %zu", ws_bytes, need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GraphWs w{};
+  graph_ws_layout(N, (int64_t)n_ids * R, n_ids, ws, ws_bytes, &w);
+  MMSBM_REQUIRE(w.bad && w.sc, MMSBM_ENOMEM, "mmsbm_graph_build_side: workspace carve-up failed");
+  if ((rc = build_one(id, other, level, N, n_ids, R, seg, adj, perm, deg, w, st))) return rc;
+  return build_schedule(deg, n_ids, N, sched, w, st);
+}

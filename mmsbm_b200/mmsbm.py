@@ -22,7 +22,7 @@ from .engine import Engine, predict_stats
 from .expectation_maximization import ExpectationMaximization
 from .helpers import get_n_per_group, structure_folds
 from .logger import setup_logger
-from .parallel import RatingShardedEngine, dist_info, gather_runs, shard_runs
+from .parallel import ShardedEngine, broadcast_seed, dist_info, gather_runs, shard_jobs, shard_runs
 
 
 class MMSBM:
@@ -44,8 +44,10 @@ class MMSBM:
         "auto" or "b200".  There is no CPU backend.
     shard : str, default="runs"  (extension; only matters under torch.distributed)
         "runs": independent runs round-robin over ranks, no per-iteration communication.
-        "ratings": every run is split by user range over all ranks, with an all-reduce of the
-        eta / pr accumulators per iteration (for one run too large or too slow for one GPU).
+        "ratings": all runs are split over all ranks by user range x item range (each rank owns
+        the ratings of its users and of its items); parameter rows travel between GPUs by
+        copy-engine DMA and one small all-reduce of the pr accumulator closes every iteration
+        (for a fit too slow or too large for one GPU; parallel.ShardedEngine).
     """
 
     data_handler = None
@@ -70,7 +72,9 @@ class MMSBM:
         assert shard in ("runs", "ratings"), "shard must be 'runs' or 'ratings'"
         self.shard = shard
 
-        self.rng = np.random.default_rng(seed)
+        # under torch.distributed every rank must draw the same child seeds and folds: with
+        # seed=None rank 0's entropy is used by all
+        self.rng = np.random.default_rng(broadcast_seed(seed))
         self.child_states = self.rng.bit_generator._seed_seq.spawn(sampling)
 
         self.logger = setup_logger("MMSBM")
@@ -78,11 +82,32 @@ class MMSBM:
         self._normalization_factors = None
         self._engine = None
         self._index_cache = None
+        self._resident = None       # run ids whose fitted parameters the engine still holds
 
     # ------------------------------------------------------------------ preparation
-    def _prepare_objects(self, train):
+    _MAX_GROUPS = 256
+    _MAX_LEVELS = 31
+
+    def _check_shape(self, n_levels):
+        """The shapes the kernels are built for, checked before any GPU work so that an
+        unsupported one fails here with the limits spelled out (the reference has none)."""
+        K, L = self.user_groups, self.item_groups
+        if K > self._MAX_GROUPS or L > self._MAX_GROUPS or n_levels > self._MAX_LEVELS:
+            raise ValueError(
+                f"mmsbm_b200 supports user_groups, item_groups <= {self._MAX_GROUPS} and at most "
+                f"{self._MAX_LEVELS} distinct ratings (got K={K}, L={L}, {n_levels} ratings); "
+                "see INTEGRATION.md, 'Supported shapes'")
+        ld = 4 * ((max(K, L) + 3) // 4)
+        if ld > 32 and n_levels * ld > 1024:
+            raise ValueError(
+                f"mmsbm_b200: with more than 32 groups on a side, ratings x groups must stay <= 1024 "
+                f"(got {n_levels} x {ld}); see INTEGRATION.md, 'Supported shapes'")
+
+    def _prepare_objects(self, train, build_engine=True):
         """Sizes, degree factors and the on-device index structure
-        (replaces src/mmsbm.py:93-146; the O((U+I)N) scans become one GPU sort)."""
+        (replaces src/mmsbm.py:93-146; the O((U+I)N) scans become one GPU sort).
+        ``build_engine=False`` (rating-sharded fits): no single-GPU index of all ratings is
+        built; the degrees come from a host bincount."""
         self.ratings = list(np.unique(train[:, 2]))          # = sorted(set(train[:, 2])), src/mmsbm.py:95
         self.r = max(self.ratings)
         self.p = int(train[:, 0].max())
@@ -97,10 +122,17 @@ class MMSBM:
         self.em = ExpectationMaximization(
             dims=self._dims, user_indices=None, item_indices=None, rating_indices=None,
             norm_factors=None, backend=self.backend, debug=self.debug)
-        self._engine = Engine(train, self.p + 1, self.m + 1, self._dims['n_ratings'],
-                              self.user_groups, self.item_groups)
-        du = np.maximum(self._engine.udeg.cpu().numpy()[:self.p + 1].astype(np.int64), 1)
-        di = np.maximum(self._engine.ideg.cpu().numpy()[:self.m + 1].astype(np.int64), 1)
+        self._check_shape(self._dims['n_ratings'])
+        self._resident = None
+        if build_engine:
+            self._engine = Engine(train, self.p + 1, self.m + 1, self._dims['n_ratings'],
+                                  self.user_groups, self.item_groups)
+            du = np.maximum(self._engine.udeg.cpu().numpy()[:self.p + 1].astype(np.int64), 1)
+            di = np.maximum(self._engine.ideg.cpu().numpy()[:self.m + 1].astype(np.int64), 1)
+        else:
+            self._engine = None
+            du = np.maximum(np.bincount(train[:, 0], minlength=self.p + 1).astype(np.int64), 1)
+            di = np.maximum(np.bincount(train[:, 1], minlength=self.m + 1).astype(np.int64), 1)
         self._normalization_factors = {
             'user': np.repeat(du[:, None], self.user_groups, axis=1),
             'item': np.repeat(di[:, None], self.item_groups, axis=1),
@@ -165,6 +197,7 @@ class MMSBM:
             engine.run(self.iterations)
         lik = engine.likelihood()
         theta, eta, pr = engine.get_params()
+        self._resident = list(run_ids) if engine is self._engine else None
         return {i: {"likelihood": np.float64(lik[j]), "pr": pr[j], "theta": theta[j], "eta": eta[j]}
                 for j, i in enumerate(run_ids)}
 
@@ -174,15 +207,19 @@ class MMSBM:
             self.logger.info(f"Running {self.sampling} runs of {self.iterations} iterations.")
         self.data_handler = DataHandler()
         train = self.data_handler.format_train_data(data)
-        self._prepare_objects(train)
         rank, world = dist_info()
         if world > 1 and self.shard == "ratings":
-            eng = RatingShardedEngine(train, self.p + 1, self.m + 1, self._dims['n_ratings'],
-                                      self.user_groups, self.item_groups)
+            self._prepare_objects(train, build_engine=False)
+            eng = ShardedEngine(train, self.p + 1, self.m + 1, self._dims['n_ratings'],
+                                self.user_groups, self.item_groups)
             every = list(range(self.sampling))
-            done = self._run_batch(eng, [self.child_states[i] for i in every], every)
+            try:
+                done = self._run_batch(eng, [self.child_states[i] for i in every], every)
+            finally:
+                eng.close()
             self.results = [done[i] for i in every]
             return
+        self._prepare_objects(train)
         mine = shard_runs(self.sampling, rank, world)
         local = self._run_batch(self._engine, [self.child_states[i] for i in mine], mine) if mine else {}
         self.results = gather_runs(local, self.sampling)
@@ -217,7 +254,12 @@ class MMSBM:
         etas = np.array([a["eta"] for a in self.results])
 
         engine = self._engine
-        engine.set_params(thetas, etas, prs)
+        if engine is None:                                    # rating-sharded fit: parameters only
+            engine = self._engine = Engine.for_prediction(self.p + 1, self.m + 1, self._dims['n_ratings'],
+                                                          self.user_groups, self.item_groups)
+        if self._resident != list(range(len(self.results))) or engine.S != len(self.results):
+            engine.set_params(thetas, etas, prs)              # else: still on the device from fit
+            self._resident = list(range(len(self.results)))
         rat = engine.prod_dist_device(test)                   # [S,M,R] on the GPU
         accuracies = [s["accuracy"] for s in predict_stats(rat, test[:, 2])]
         best = accuracies.index(max(accuracies))
@@ -323,8 +365,7 @@ class MMSBM:
         shard_jobs = world > 1 and self.shard == "runs"
         done = {}
         if shard_jobs:
-            jobs = [(f, s) for f in range(folds) for s in range(self.sampling)]
-            mine = jobs[rank::world]
+            mine = shard_jobs(folds, self.sampling, rank, world)
             local = {}
             for f in sorted({f for f, _ in mine}):
                 self.data_handler = DataHandler()
@@ -345,6 +386,7 @@ class MMSBM:
                 self.data_handler = DataHandler()
                 self._prepare_objects(self.data_handler.format_train_data(train))
                 self.results = [done[(f, s)] for s in range(self.sampling)]
+                self._resident = None
             else:
                 self.fit(train, silent=True)
             self.prediction_matrix = self.predict(test)

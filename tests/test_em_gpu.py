@@ -148,7 +148,11 @@ def test_fixture_one_and_ten_iterations(golden_dir):
 
 @pytest.mark.parametrize("K,L,R,S", [(10, 10, 5, 3), (20, 20, 5, 2), (7, 5, 4, 1), (3, 32, 6, 2), (33, 9, 5, 1),
                                      (1, 1, 2, 1), (64, 48, 5, 1), (130, 70, 3, 1), (12, 28, 10, 2), (20, 20, 5, 5),
-                                     (20, 20, 5, 8), (7, 18, 4, 7), (20, 19, 3, 13)])
+                                     (20, 20, 5, 8), (7, 18, 4, 7), (20, 19, 3, 13),
+                                     # the BASELINE.json shapes the kernels specialise on: Netflix
+                                     # (K=L=32, one run: 8-lane rows on both sides), ML-1M (K=L=10, eight
+                                     # runs: pairs of 3-lane rows), ML-100K (K=L=10, one run)
+                                     (32, 32, 5, 1), (10, 10, 5, 8), (10, 10, 5, 1)])
 @pytest.mark.parametrize("heavy", [False, True])
 def test_batched_runs_one_iteration_vs_oracle(K, L, R, S, heavy):
     from mmsbm_b200.engine import Engine
@@ -570,3 +574,28 @@ def test_full_size_invariants(shape):
     _, re_, _ = orc.em_sums(rows, theta[0], eta[0], pr[0])
     degi = np.bincount(data[:, 1], minlength=I)
     assert rel_err(et[0][items] * np.maximum(degi[items], 1)[:, None], re_[items]) < PARAM_TOL
+
+
+# ------------------------------------------------------------- sharded runs (one rank here)
+@pytest.mark.parametrize("K,L,S", [(20, 20, 8), (32, 32, 1), (10, 10, 3), (7, 5, 2)])
+def test_sharded_engine_with_one_rank_equals_engine(K, L, S):
+    """mmsbm_em_run_sharded with world = 1 (own ranges = everything, no peers, no collective) walks
+    the same kernels over tables kept in the exchange buffer: bit-identical to mmsbm_em_run."""
+    from mmsbm_b200.engine import Engine
+    from mmsbm_b200.parallel import ShardedEngine
+    N, U, I, R = 50000, 600, 400, 5
+    data = random_triples(91, N, U, I, R, heavy_tail=True)
+    theta, eta, pr = random_params(93, U, I, K, L, R, S=S)
+    a = Engine(data, U, I, R, K, L)
+    a.set_params(theta, eta, pr)
+    a.run(5)
+    b = ShardedEngine(data, U, I, R, K, L)
+    b.set_params(theta, eta, pr)
+    b.run(3)
+    b.run(2)                                                 # odd + even: both halves of the tables
+    for x, y in zip(a.get_params(), b.get_params()):
+        np.testing.assert_array_equal(x, y)
+    np.testing.assert_array_equal(a.likelihood(), b.likelihood())
+    ms = b.run(2, prof=True)
+    assert ms[0] > 0.0
+    b.close()

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(_lib.EXPORTS) == declared
-    assert lib.mmsbm_abi_version() == 3
+    assert lib.mmsbm_abi_version() == 4
 
 
 def test_no_cpu_fallback_without_device():
