@@ -83,6 +83,7 @@ class MMSBM:
         self._engine = None
         self._index_cache = None
         self._resident = None       # run ids whose fitted parameters the engine still holds
+        self.timings = {}           # wall seconds of the stages of the last fit
 
     # ------------------------------------------------------------------ preparation
     _MAX_GROUPS = 256
@@ -180,10 +181,36 @@ class MMSBM:
         return theta, eta, pr
 
     # -------------------------------------------------------------------------- fit
+    def _tick(self, stage, t0):
+        """Wall seconds of a stage of the last fit, accumulated in ``self.timings`` (bench.py's
+        api_e2e reports them; the device is synchronised so the split is meaningful)."""
+        import time
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        now = time.perf_counter()
+        self.timings[stage] = self.timings.get(stage, 0.0) + (now - t0)
+        return now
+
+    def _initial_batch(self, seeds):
+        """theta0/eta0/pr0 of several runs, stacked.  The draws of different runs come from
+        independent generators (one SeedSequence child each), so they run in threads (numpy's
+        Generator releases the GIL while filling an array); every run's stream is untouched."""
+        if len(seeds) > 1 and (self.p + 1) * self.user_groups >= 200_000:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=min(len(seeds), 8)) as ex:
+                inits = list(ex.map(self._initial_parameters, seeds))
+        else:
+            inits = [self._initial_parameters(s) for s in seeds]
+        return tuple(np.stack([a[j] for a in inits]) for j in range(3))
+
     def _run_batch(self, engine, seeds, run_ids):
-        inits = [self._initial_parameters(s) for s in seeds]
-        engine.set_params(np.stack([a[0] for a in inits]), np.stack([a[1] for a in inits]),
-                          np.stack([a[2] for a in inits]))
+        import time
+        t = time.perf_counter()
+        theta0, eta0, pr0 = self._initial_batch(seeds)
+        t = self._tick("init_draws", t)
+        engine.set_params(theta0, eta0, pr0)
+        t = self._tick("params_h2d", t)
         if self.debug:
             done = 0
             while done < self.iterations:
@@ -195,8 +222,11 @@ class MMSBM:
                         self.logger.debug(f"\nLikelihood at run {i} is {lik:.0f}")
         else:
             engine.run(self.iterations)
+        t = self._tick("em_iterations", t)
         lik = engine.likelihood()
+        t = self._tick("likelihood", t)
         theta, eta, pr = engine.get_params()
+        t = self._tick("results_d2h", t)
         self._resident = list(run_ids) if engine is self._engine else None
         return {i: {"likelihood": np.float64(lik[j]), "pr": pr[j], "theta": theta[j], "eta": eta[j]}
                 for j, i in enumerate(run_ids)}
@@ -205,8 +235,12 @@ class MMSBM:
         """Fit ``sampling`` EM runs on a DataFrame with columns [users, items, ratings]."""
         if not silent:
             self.logger.info(f"Running {self.sampling} runs of {self.iterations} iterations.")
+        import time
+        self.timings = {}
+        t = time.perf_counter()
         self.data_handler = DataHandler()
         train = self.data_handler.format_train_data(data)
+        t = self._tick("encode", t)
         rank, world = dist_info()
         if world > 1 and self.shard == "ratings":
             self._prepare_objects(train, build_engine=False)
@@ -220,6 +254,7 @@ class MMSBM:
             self.results = [done[i] for i in every]
             return
         self._prepare_objects(train)
+        self._tick("rows_h2d_index_build", t)
         mine = shard_runs(self.sampling, rank, world)
         local = self._run_batch(self._engine, [self.child_states[i] for i in mine], mine) if mine else {}
         self.results = gather_runs(local, self.sampling)

@@ -1,8 +1,11 @@
 """Multi-GPU checks, launched by tests/test_multi_gpu.py under torchrun (one rank per GPU):
   1. MMSBM.fit with runs sharded over ranks == the same fit in one process (bit-identical:
      runs are independent and every sum has a fixed order);
-  2. MMSBM.fit(shard="ratings") (user-range shards + NCCL all-reduce of n_eta / n_pr per
-     iteration) == the unsharded fit within 1e-10 per element, likelihood within 1e-8."""
+  2. MMSBM.fit(shard="ratings") (user-range x item-range shards, copy-engine exchange of the
+     parameter rows, one NCCL all-reduce of n_pr per iteration: mmsbm_em_run_sharded) == the
+     unsharded fit within 1e-9 per element after 12 iterations, likelihood within 1e-8;
+  3. cv_fit with the folds x runs jobs sharded == serial folds;
+  4. ShardedEngine at the BASELINE kernel shapes vs the one-GPU loop."""
 import os
 import sys
 
@@ -69,9 +72,33 @@ def main():
     c = MMSBM(2, 2, iterations=10, sampling=3, seed=1)
     got_acc = [float(a) for a in c.cv_fit(mock_data(1), folds=2)]
     assert got_acc == want_acc, (got_acc, want_acc)
+    # 4. the sharded loop itself at the shapes its kernels specialise on (six runs + a pair per warp
+    #    at K=L=20; 8-lane rows, one run at K=L=32), heavy-tailed ids, against the one-GPU loop
+    from mmsbm_b200.parallel import ShardedEngine
+    from tests.util import random_params, random_triples
+    worst2 = 0.0
+    for (K2, L2, S2) in ((20, 20, 8), (32, 32, 1), (10, 10, 3)):
+        N2, U2, I2, R2 = 120000, 3000, 700, 5
+        data = random_triples(7, N2, U2, I2, R2, heavy_tail=True)
+        th, et, pr = random_params(9, U2, I2, K2, L2, R2, S=S2)
+        one = Engine(data, U2, I2, R2, K2, L2)
+        one.set_params(th, et, pr)
+        one.run(7)
+        w_th, w_et, w_pr = one.get_params()
+        w_lik = one.likelihood()
+        sh = ShardedEngine(data, U2, I2, R2, K2, L2)
+        sh.set_params(th, et, pr)
+        sh.run(4)
+        sh.run(3)
+        g_th, g_et, g_pr = sh.get_params()
+        g_lik = sh.likelihood()
+        sh.close()
+        worst2 = max(worst2, rel_err(g_th, w_th), rel_err(g_et, w_et), rel_err(g_pr, w_pr))
+        assert np.max(np.abs(g_lik - w_lik) / np.abs(w_lik)) < 1e-8, (K2, g_lik, w_lik)
+    assert worst2 < 1e-9, worst2
     dist.barrier()
     if rank == 0:
-        print(f"multi-gpu ok: world={dist.get_world_size()} rating-sharded worst rel err {worst:.2e}")
+        print(f"multi-gpu ok: world={dist.get_world_size()} rating-sharded worst rel err {worst:.2e} / {worst2:.2e}")
     dist.destroy_process_group()
 
 

@@ -232,7 +232,10 @@ def test_bench_reference_arm_runs_without_a_gpu(backend):
     assert line["impl"] == "reference" and line["metric"] == "rating-updates/sec" and line["value"] > 0
     assert line["unit"] == "rating-updates/s" and line["higher_is_better"] is True
     assert line["config"]["workload"] == "ml100k" and line["gpu_launches"] == 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["backend"] == backend
+    # the unmodified reference when baseline/_ref is installed (oracle/install_reference.py), else the port
+    have_ref = os.path.exists(os.path.join(root, "baseline", "_ref", "kernels_numpy.py"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert line["cpu_baseline"]["backend"] == backend
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0,
                            "d2h_bytes_per_step": 0}
 
@@ -246,5 +249,6 @@ def test_bench_algorithmic_bytes_match_the_survey_table():
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     want = {"ml100k": 180.2, "ml1m": 163.6, "ml20m": 324.6, "netflix": 530.5}
-    for name, (U, I, N, K, L, S) in bench.WORKLOADS.items():
-        assert abs(bench.b_alg(U, I, N, K, L, S) - want[name]) < 0.06, name
+    for name, want_b in want.items():
+        U, I, N, K, L, S = bench.WORKLOADS[name]
+        assert abs(bench.b_alg(U, I, N, K, L, S) - want_b) < 0.06, name
