@@ -240,6 +240,12 @@ int mmsbm_compute_omegas(const int32_t* user_dev, const int32_t* item_dev, const
                          double* omegas_dev, void* stream);
 
 /* ================= host-pointer entry points (what the ctypes stub binds) ================= */
+/* update_coefficients and likelihood keep the index structure of the LAST data array on the device,
+ * keyed on its content (device, N, U, I, R, 64-bit checksum of the 24*N bytes): the reference's loop
+ * (src/mmsbm.py:243-250) passes the same array every iteration, so only the first call uploads
+ * and sorts it.  An array modified in place misses.  MMSBM_INDEX_CACHE=0 disables the cache. */
+int mmsbm_index_cache_stats(int64_t* hits, int64_t* misses);
+int mmsbm_index_cache_clear(void);
 /* plugin b1 (src/backend.py:22): numpy in, numpy out, data int64 [N,3] */
 int mmsbm_host_compute_omegas(const int64_t* data, int64_t n_ratings,
                               const double* theta, int32_t n_users, int32_t K,

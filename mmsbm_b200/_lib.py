@@ -64,6 +64,8 @@ _PROTOS = {
     "mmsbm_predict_stats": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mmsbm_mean_over_runs": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "mmsbm_compute_omegas": (C.c_int, [_vp] * 3 + [_i64, _i32, _i32, _i32] + [_vp] * 4 + [_vp]),
+    "mmsbm_index_cache_stats": (C.c_int, [C.POINTER(_i64), C.POINTER(_i64)]),
+    "mmsbm_index_cache_clear": (C.c_int, []),
     "mmsbm_host_compute_omegas": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp]),
     "mmsbm_host_update_coefficients": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32,
                                                  _vp, _vp, _vp]),

@@ -397,9 +397,9 @@ class MMSBM:
         jobs shard over the ranks; the result is the same."""
         pairs = self._make_folds(data, folds)
         rank, world = dist_info()
-        shard_jobs = world > 1 and self.shard == "runs"
+        sharded_cv = world > 1 and self.shard == "runs"
         done = {}
-        if shard_jobs:
+        if sharded_cv:
             mine = shard_jobs(folds, self.sampling, rank, world)
             local = {}
             for f in sorted({f for f, _ in mine}):
@@ -417,7 +417,7 @@ class MMSBM:
         all_results = []
         for f, (train, test) in enumerate(pairs):
             self.logger.info(f"Running fold {f + 1} of {folds}...")
-            if shard_jobs:
+            if sharded_cv:
                 self.data_handler = DataHandler()
                 self._prepare_objects(self.data_handler.format_train_data(train))
                 self.results = [done[(f, s)] for s in range(self.sampling)]
