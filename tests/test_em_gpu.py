@@ -539,6 +539,9 @@ def test_reference_loader_contract():
     dict(name="ML-1M", N=1_000_000, U=6040, I=3706, K=10, L=10, S=8),
     dict(name="ML-20M", N=20_000_000, U=138_000, I=27_000, K=20, L=20, S=2),
     dict(name="ML-20M six runs per warp + a single", N=20_000_000, U=138_000, I=27_000, K=20, L=20, S=7),
+    dict(name="ML-20M sampling=8 (the bench configuration: six runs + a pair)", N=20_000_000, U=138_000,
+         I=27_000, K=20, L=20, S=8),
+    dict(name="ML-100K (per-CTA piece ranges, one run)", N=100_000, U=943, I=1682, K=10, L=10, S=1),
 ])
 def test_full_size_invariants(shape):
     """At sizes the oracle cannot reach, check what must hold for any input: each rating
@@ -558,22 +561,122 @@ def test_full_size_invariants(shape):
     for s in range(S):
         assert abs(npr[s].sum() - N) <= 1e-9 * N
     nth = raw[0].cpu().numpy()[..., :K]
+    net = raw[1].cpu().numpy()[..., :L]
     deg = np.bincount(data[:, 0], minlength=U)
     np.testing.assert_allclose(nth.sum(axis=2), np.broadcast_to(deg, (S, U)), rtol=1e-11)
+    # marginals that tie n_pr to the other two sums for EVERY run: all three are sums of the same
+    # increments inc[n,k,l], so  sum_lr n_pr[k,l,r] = sum_u n_theta[u,k],  sum_kr n_pr[k,l,r] =
+    # sum_i n_eta[i,l],  and  sum_kl n_pr[k,l,r] = number of ratings at level r
+    levels = np.bincount(data[:, 2], minlength=R)
+    for s in range(S):
+        np.testing.assert_allclose(npr[s].sum(axis=(1, 2)), nth[s].sum(axis=0), rtol=1e-10)
+        np.testing.assert_allclose(npr[s].sum(axis=(0, 2)), net[s].sum(axis=0), rtol=1e-10)
+        np.testing.assert_allclose(npr[s].sum(axis=(0, 1)), levels, rtol=1e-10)
     e.run(1)
     th, et, prn = e.get_params()
     np.testing.assert_allclose(th.sum(axis=2), 1.0, rtol=1e-11)
     np.testing.assert_allclose(et.sum(axis=2), 1.0, rtol=1e-11)
     np.testing.assert_allclose(prn.sum(axis=3), 1.0, rtol=1e-11)
     users = np.array([0, 1, U // 2, U - 1])
-    rows = data[np.isin(data[:, 0], users)]
-    rt, _, _ = orc.em_sums(rows, theta[0], eta[0], pr[0])
-    assert rel_err(th[0][users] * np.maximum(deg[users], 1)[:, None], rt[users]) < PARAM_TOL
+    rows_u = data[np.isin(data[:, 0], users)]
     items = np.array([0, I // 3, I - 1])
-    rows = data[np.isin(data[:, 1], items)]
-    _, re_, _ = orc.em_sums(rows, theta[0], eta[0], pr[0])
+    rows_i = data[np.isin(data[:, 1], items)]
     degi = np.bincount(data[:, 1], minlength=I)
-    assert rel_err(et[0][items] * np.maximum(degi[items], 1)[:, None], re_[items]) < PARAM_TOL
+    for s in range(S):                                       # every run, not only the first
+        rt, _, _ = orc.em_sums(rows_u, theta[s], eta[s], pr[s])
+        assert rel_err(th[s][users] * np.maximum(deg[users], 1)[:, None], rt[users]) < PARAM_TOL
+        _, re_, _ = orc.em_sums(rows_i, theta[s], eta[s], pr[s], chunk=20000)
+        assert rel_err(et[s][items] * np.maximum(degi[items], 1)[:, None], re_[items]) < PARAM_TOL
+
+
+def test_ml20m_eight_runs_restricted_problem_vs_oracle():
+    """n_pr (and everything else) of the ML-20M bench configuration -- K = L = 20, sampling = 8, the
+    full 138k x 27k id ranges, so the six-run + pair kernels and the full-size tables -- element by
+    element against the oracle, on a 2e5-row restriction of the ratings that the oracle finishes in
+    seconds; once with the per-CTA piece ranges a problem of this size gets by default and once
+    with the launch-wide piece queue the full-size problem uses."""
+    import os
+    from mmsbm_b200.engine import Engine
+    U, I, K, L, S, R, n = 138_000, 27_000, 20, 20, 8, 5, 200_000
+    rows = random_triples(61, n, U, I, R)            # n >= U: every user id appears at least once
+    theta, eta, pr = random_params(67, U, I, K, L, R, S=S)
+    fu, fi = orc.degree_factors(rows, K, L)
+    want = [orc.em_iteration(rows, theta[s], eta[s], pr[s], fu, fi, chunk=20000) for s in range(S)]
+    want_lik = [sum(orc.likelihood(rows[lo:lo + 20000], *want[s]) for lo in range(0, n, 20000)) for s in range(S)]
+    for dyn in ("0", "1"):
+        os.environ["MMSBM_DYN"] = dyn
+        try:
+            e = Engine(rows, U, I, R, K, L)
+            e.set_params(theta, eta, pr)
+            e.run(1)
+            th, et, prn = e.get_params()
+            lik = e.likelihood()
+        finally:
+            del os.environ["MMSBM_DYN"]
+        worst = 0.0
+        for s in range(S):
+            worst = max(worst, rel_err(th[s], want[s][0]), rel_err(et[s], want[s][1]), rel_err(prn[s], want[s][2]))
+            assert abs(lik[s] - want_lik[s]) <= LIK_TOL * abs(want_lik[s])
+        print(f"ML-20M S=8 restricted, piece queue={dyn}: worst rel err {worst:.3e}")
+        assert worst < PARAM_TOL
+
+
+def test_ml100k_full_fit_likelihood_vs_oracle():
+    """BASELINE.json configs[0] in full: 943 x 1682, 1e5 ratings, K = L = 10, one run, 200 iterations
+    from the reference's seeded init (src/mmsbm.py:224-233), GPU loop (CUDA-graph replay of
+    iteration pairs) against the oracle's loop.  Final likelihood within 1e-8 relative
+    (north_star); the drift of theta / eta / pr after 200 iterations is printed and bounded."""
+    from mmsbm_b200.engine import Engine
+    U, I, N, K, L, R, T = 943, 1682, 100_000, 10, 10, 5, 200
+    data = random_triples(71, N, U, I, R, heavy_tail=True)
+    fu, fi = orc.degree_factors(data, K, L)
+    _, kids = orc.child_seeds(1, 1)
+    th, et, pr = orc.seeded_init(kids[0], U, I, K, L, R, fu, fi)
+    e = Engine(data, U, I, R, K, L)
+    e.set_params(th[None], et[None], pr[None])
+    e.run(T)
+    g_th, g_et, g_pr = e.get_params()
+    g_lik = e.likelihood()[0]
+    for _ in range(T):
+        th, et, pr = orc.em_iteration(data, th, et, pr, fu, fi)
+    want = orc.likelihood(data, th, et, pr)
+    drift = (float(np.max(np.abs(g_th[0] - th))), float(np.max(np.abs(g_et[0] - et))), float(np.max(np.abs(g_pr[0] - pr))))
+    print(f"ML-100K x {T} iterations: likelihood {g_lik!r} vs {want!r} (rel {abs(g_lik - want) / abs(want):.2e}), "
+          f"max abs drift theta/eta/pr {drift}")
+    assert abs(g_lik - want) <= LIK_TOL * abs(want)
+    assert max(drift) < 1e-8
+
+
+def test_ml1m_eight_runs_same_best_sample_as_oracle():
+    """BASELINE.json configs[1] shape (6040 x 3706, 1e6 ratings, K = L = 10, sampling = 8): after two
+    iterations of every run from the reference's seeded init, the per-run accuracy counts on a
+    held-out set, the predicted ratings (bit-exact) and hence the run ``predict`` selects
+    (src/mmsbm.py:306,474-478) are the oracle's."""
+    from mmsbm_b200.engine import Engine, predict_stats
+    U, I, N, K, L, R, S, T = 6040, 3706, 1_000_000, 10, 10, 5, 8, 2
+    data = random_triples(73, N, U, I, R)
+    test = random_triples(79, 100_000, U, I, R)
+    fu, fi = orc.degree_factors(data, K, L)
+    _, kids = orc.child_seeds(1, S)
+    inits = [orc.seeded_init(k, U, I, K, L, R, fu, fi) for k in kids]
+    e = Engine(data, U, I, R, K, L)
+    e.set_params(*(np.stack([a[j] for a in inits]) for j in range(3)))
+    e.run(T)
+    stats, pred = predict_stats(e.prod_dist_device(test), test[:, 2], want_pred=True)
+    lik = e.likelihood()
+    acc_gpu = [s["accuracy"] for s in stats]
+    acc_cpu = []
+    for s in range(S):
+        th, et, pr = inits[s]
+        for _ in range(T):
+            th, et, pr = orc.em_iteration(data, th, et, pr, fu, fi, chunk=100_000)
+        rat = orc.rating_distribution(test, th, et, pr)
+        np.testing.assert_array_equal(pred[s], np.argmax(rat, axis=1))
+        acc_cpu.append(orc.prediction_stats(rat, test[:, 2], list(range(R)))["accuracy"])
+        want = sum(orc.likelihood(data[lo:lo + 100_000], th, et, pr) for lo in range(0, N, 100_000))
+        assert abs(lik[s] - want) <= LIK_TOL * abs(want)
+    assert acc_gpu == acc_cpu
+    assert acc_gpu.index(max(acc_gpu)) == acc_cpu.index(max(acc_cpu))
 
 
 # ------------------------------------------------------------- sharded runs (one rank here)
