@@ -825,6 +825,11 @@ extern "C" int mmsbm_em_workspace_bytes(int64_t N, int32_t U, int32_t I, int32_t
 struct Overlap {
   cudaStream_t side = nullptr;
   cudaEvent_t e[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // Launch-bound sizes: the user side and the item side of an iteration only meet at the P tables,
+  // so they run as two independent branches (main stream: w, by-user pass, n of the users; side
+  // stream: w, by-item pass, n of the items), pr on the branch that emits it.  The critical path of
+  // an iteration drops from 13 dependent kernels to 7, and the two passes fill the GPU together.
+  bool two_branch = false;
 };
 
 static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t* udeg,
@@ -873,6 +878,41 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
 #define MMSBM_JOIN(k) do { if (ov) { MMSBM_CUDA(cudaEventRecord(ov->e[k], s2)); \
                                      MMSBM_CUDA(cudaStreamWaitEvent(st, ov->e[k], 0)); } } while (0)
 #define MMSBM_SIDE_DONE(k) do { if (ov) MMSBM_CUDA(cudaEventRecord(ov->e[k], s2)); } while (0)
+  if (ov && ov->two_branch) {
+    if (dyn) MMSBM_CUDA(cudaMemsetAsync(counters, 0, d.ctr_elems * 4, st));
+    if ((rc = launch_prep_p(pr, K, L, R, d.ldk, d.ldl, S, pw_u, pn_u, pw_i, pn_i, st))) return rc;
+    MMSBM_FORK(0);
+    auto pr_step = [&](cudaStream_t s) {
+      return launch_pr(d.emit_items ? eta : theta, d.emit_items ? wg_i : wg_u, partial, pr, pr_out, d.nseg_e,
+                       d.NA_e, d.emit_items ? d.ldl : d.ldk, d.NBp_e, K, L, R, S, d.emit_items,
+                       (flags & MMSBM_RAW_ETA_PR) == 0, s);
+    };
+    // user branch (main stream)
+    if (hexa_enabled(d.ldl, S) && (rc = launch_interleave(eta, et6, I, I, 0, d.ldl, 0, S / 6, 6, st))) return rc;
+    if (pairs_enabled(d.ldl, S) && (rc = launch_interleave(eta, et2, I, I, 0, d.ldl, 0, S / 2, 2, st))) return rc;
+    if ((rc = launch_w(theta, pw_u, wg_u, U, d.ldk, d.rnb_u, S, st))) return rc;
+    {
+      SegArgs a{useg, uadj, usched, eta, wg_u, slots_u, d.pmax_u, d.lmax, d.smax, U, I, d.ldl, R, 0, 0, 0,
+                dyn ? counters : nullptr};
+      if ((rc = launch_segment_pass_and_fixup(a, et2, et6, N, S, st))) return rc;
+    }
+    if ((rc = launch_n(wg_u, pn_u, theta, udeg, theta_out, U, d.ldk, d.rnb_u,
+                       (flags & MMSBM_RAW_THETA) ? 0 : 1, S, st))) return rc;
+    if (!d.emit_items && (rc = pr_step(st))) return rc;
+    // item branch (side stream)
+    if (pairs_enabled(d.ldk, S) && (rc = launch_interleave(theta, th2, U, U, 0, d.ldk, 0, S / 2, 2, s2))) return rc;
+    if ((rc = launch_w(eta, pw_i, wg_i, I, d.ldl, d.rnb_i, S, s2))) return rc;
+    {
+      SegArgs a{iseg, iadj, isched, theta, wg_i, slots_i, d.pmax_i, d.lmax, d.smax, I, U, d.ldk, R, 0, 0, 0,
+                dyn ? counters + d.ctr_elems / 2 : nullptr};
+      if ((rc = launch_segment_pass_and_fixup(a, th2, nullptr, N, S, s2))) return rc;
+    }
+    if ((rc = launch_n(wg_i, pn_i, eta, ideg, eta_out, I, d.ldl, d.rnb_i,
+                       (flags & MMSBM_RAW_ETA_PR) ? 0 : 1, S, s2))) return rc;
+    if (d.emit_items && (rc = pr_step(s2))) return rc;
+    MMSBM_JOIN(1);
+    return 0;
+  }
   // ---- P tables and w = own x Pw for every user and item ----
   {
     if (dyn) MMSBM_CUDA(cudaMemsetAsync(counters, 0, d.ctr_elems * 4, st));   // piece queues of both passes
@@ -980,11 +1020,11 @@ extern "C" int mmsbm_em_run(const int32_t* useg, const int32_t* uadj, const int3
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Overlap ov;
   const bool small = (double)N * S < 5.0e7;
-  const bool overlap = (!small || getenv("MMSBM_FORCE_OVERLAP") != nullptr) && iterations > 0 &&
-                       getenv("MMSBM_NO_OVERLAP") == nullptr;
+  const bool overlap = iterations > 0 && getenv("MMSBM_NO_OVERLAP") == nullptr;
   if (overlap) {
     MMSBM_CUDA(cudaStreamCreateWithFlags(&ov.side, cudaStreamNonBlocking));
     for (auto& e : ov.e) MMSBM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ov.two_branch = small && getenv("MMSBM_FORCE_OVERLAP") == nullptr;
   }
   auto step = [&](bool fwd) {
     return em_step_impl(useg, uadj, udeg, iseg, iadj, ideg, usched, isched, N, U, I, R, K, L, S,
@@ -1003,7 +1043,7 @@ extern "C" int mmsbm_em_run(const int32_t* useg, const int32_t* uadj, const int3
   // Launch-bound sizes (a few 10 us of kernels per iteration): capture one a->b->a pair of
   // iterations into a CUDA graph and replay it; the graph lives only inside this call.
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  if (small && !overlap && getenv("MMSBM_NO_GRAPH") == nullptr && iterations >= 8 && st != nullptr && cudaStreamIsCapturing(st, &cap) == cudaSuccess &&
+  if (small && getenv("MMSBM_NO_GRAPH") == nullptr && iterations >= 8 && st != nullptr && cudaStreamIsCapturing(st, &cap) == cudaSuccess &&
       cap == cudaStreamCaptureStatusNone) {
     int rc = step(true);                       // first pair uncaptured: sets function attributes
     if (rc == 0) rc = step(false);
