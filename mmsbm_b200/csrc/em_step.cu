@@ -260,7 +260,10 @@ __global__ void __launch_bounds__(kRowThreads) row_w_kernel(const double* __rest
   }
 }
 
-template <int LD, int ROWS>
+// PF chunks (32 bytes each) of the G row are loaded back to back before any of them is used: a lane
+// then has PF loads in flight instead of one, which is what the HBM stream of this kernel needs
+// (lane-per-row rows are 800 bytes apart, so memory-level parallelism has to come from depth).
+template <int LD, int ROWS, int PF>
 __global__ void __launch_bounds__(kRowThreads) row_n_kernel(const double* __restrict__ G,
                                                             const double* __restrict__ pn,
                                                             const double* __restrict__ own,
@@ -290,22 +293,30 @@ __global__ void __launch_bounds__(kRowThreads) row_n_kernel(const double* __rest
 #pragma unroll
       for (int a = 0; a < LD; ++a) acc[j][a] = 0.0;
     }
-    for (int ob = 0; ob < RNB; ob += 4) {
-      double gv[ROWS][4];
+    for (int ob0 = 0; ob0 < RNB; ob0 += 4 * PF) {             // RNB is a multiple of 4 * PF (host checks)
+      double4_t gq[ROWS][PF];
 #pragma unroll
-      for (int j = 0; j < ROWS; ++j) {
-        const double4_t gq = ldg256(grow[j] + ob);
-        gv[j][0] = gq.x; gv[j][1] = gq.y; gv[j][2] = gq.z; gv[j][3] = gq.w;
-      }
+      for (int j = 0; j < ROWS; ++j)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+        for (int p = 0; p < PF; ++p) gq[j][p] = ldg256(grow[j] + ob0 + 4 * p);
 #pragma unroll
-        for (int c = 0; c < LD / 4; ++c) {
-          const double4_t p = lds32(Ps + (ob + i) * LD + 4 * c);
+      for (int p = 0; p < PF; ++p) {
+        const int ob = ob0 + 4 * p;
+        double gv[ROWS][4];
 #pragma unroll
-          for (int j = 0; j < ROWS; ++j) {
-            acc[j][4 * c] = fma(gv[j][i], p.x, acc[j][4 * c]);         acc[j][4 * c + 1] = fma(gv[j][i], p.y, acc[j][4 * c + 1]);
-            acc[j][4 * c + 2] = fma(gv[j][i], p.z, acc[j][4 * c + 2]); acc[j][4 * c + 3] = fma(gv[j][i], p.w, acc[j][4 * c + 3]);
+        for (int j = 0; j < ROWS; ++j) {
+          gv[j][0] = gq[j][p].x; gv[j][1] = gq[j][p].y; gv[j][2] = gq[j][p].z; gv[j][3] = gq[j][p].w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int c = 0; c < LD / 4; ++c) {
+            const double4_t pv = lds32(Ps + (ob + i) * LD + 4 * c);
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) {
+              acc[j][4 * c] = fma(gv[j][i], pv.x, acc[j][4 * c]);         acc[j][4 * c + 1] = fma(gv[j][i], pv.y, acc[j][4 * c + 1]);
+              acc[j][4 * c + 2] = fma(gv[j][i], pv.z, acc[j][4 * c + 2]); acc[j][4 * c + 3] = fma(gv[j][i], pv.w, acc[j][4 * c + 3]);
+            }
           }
         }
       }
@@ -701,20 +712,31 @@ int launch_n(const double* G, const double* pn, const double* own, const int32_t
   const size_t smem = (size_t)LD * RNB * 8;
   // one row per lane here: two rows cost occupancy (142 registers) and measured slower
   const int rows_env = env_int("MMSBM_ROWS_N", 1);
-#define MMSBM_ROW_N(LDv)                                                                        \
-  if (LD == LDv && smem <= 200 * 1024) {                                                        \
-    constexpr int kRows = (LDv <= 24) ? 2 : 1;   /* 2 x LD accumulator registers per lane */      \
-    const bool two = kRows == 2 && rows_env == 2;                                               \
-    auto kern = two ? row_n_kernel<LDv, kRows> : row_n_kernel<LDv, 1>;                          \
-    const int per = kRowThreads * (two ? 2 : 1);                                                \
-    const int gx = min((M + per - 1) / per, sm_count() * 2);                                           \
+  // chunks in flight per lane: MMSBM_ROWN_PF (1 = round-1 behaviour); needs (RNB / 4) % PF == 0
+  int pf = env_int("MMSBM_ROWN_PF", 5);
+  if (pf != 1 && pf != 2 && pf != 5) pf = 1;
+  if ((RNB / 4) % pf != 0) pf = ((RNB / 4) % 2 == 0 && pf != 1) ? 2 : 1;
+#define MMSBM_ROW_N_GO(kern, two)                                                               \
+  {                                                                                             \
+    const int per = kRowThreads * ((two) ? 2 : 1);                                              \
+    const int gx = min((M + per - 1) / per, sm_count() * 2);                                    \
     MMSBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<dim3(gx, n_runs), kRowThreads, smem, st>>>(G, pn, own, deg, out, M, RNB, normalize); \
     MMSBM_LAUNCH_CHECK("row_n_kernel");                                                         \
     return 0;                                                                                   \
   }
+#define MMSBM_ROW_N(LDv)                                                                        \
+  if (LD == LDv && smem <= 200 * 1024) {                                                        \
+    constexpr int kRows = (LDv <= 24) ? 2 : 1;   /* 2 x LD accumulator registers per lane */      \
+    const bool two = kRows == 2 && rows_env == 2;                                               \
+    if (two) MMSBM_ROW_N_GO((row_n_kernel<LDv, kRows, 1>), true)                                \
+    if (pf == 5) MMSBM_ROW_N_GO((row_n_kernel<LDv, 1, 5>), false)                               \
+    if (pf == 2) MMSBM_ROW_N_GO((row_n_kernel<LDv, 1, 2>), false)                               \
+    MMSBM_ROW_N_GO((row_n_kernel<LDv, 1, 1>), false)                                            \
+  }
   MMSBM_ROW_N(4) MMSBM_ROW_N(8) MMSBM_ROW_N(12) MMSBM_ROW_N(16) MMSBM_ROW_N(20) MMSBM_ROW_N(24)
   MMSBM_ROW_N(28) MMSBM_ROW_N(32)
+#undef MMSBM_ROW_N_GO
 #undef MMSBM_ROW_N
   GemmArgs g{G, pn, out, own, deg, M, LD, RNB, RNB, 0, normalize, 0};
   return launch_gemm<true>(g, n_runs, st);

@@ -7,12 +7,13 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "em_internal.cuh"    // sm_count()
 #include "segment_pass.cuh"   // double4_t, ldg256, GroupSum (lane groups of the row gathers)
 
 namespace mmsbm {
 
 constexpr int kLikWarps = 8;
-constexpr int kLikCtas = 148 * 4;   // persistent CTAs per run
+constexpr int kLikCtas = 148 * 4;   // CTAs per run of the element-wise kernel (sizes its partial-sum buffer; a B200 has 148 SMs)
 
 // ---- likelihood ----------------------------------------------------------------------------
 // sum_n sum_kl w~ (log w~ - log S~_n), w~ = max(theta_k eta_l pr_klr, eps), S~ = max(sum w, eps).
@@ -474,7 +475,7 @@ static int launch_lik_tables(const double* theta, const double* pr, double* W, d
   const int ldl = row_stride(L);
   const size_t smem = 2 * (size_t)LD * R * ldl * 8;
   MMSBM_CUDA(cudaFuncSetAttribute(lik_user_tables_kernel<LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int gx = (U + 255) / 256 < 148 * 2 ? (U + 255) / 256 : 148 * 2;
+  const int gx = (U + 255) / 256 < sm_count() * 2 ? (U + 255) / 256 : sm_count() * 2;
   lik_user_tables_kernel<LD><<<dim3(gx, nb), 256, smem, st>>>(theta, pr, W, A, U, K, L, R, ldl, run0);
   MMSBM_LAUNCH_CHECK("lik_user_tables_kernel");
   return 0;
@@ -520,7 +521,8 @@ static int likelihood_factorised(const int32_t* useg, const int32_t* uadj, const
     if (rc) return rc;
     LikPassArgs a{useg, uadj, usched, e2, W, A, partial + (size_t)run0 * pmax, pmax, U, I, R};
     const int64_t want = (pmax + 7) / 8;
-    const dim3 grid((unsigned)(want < 148 * 16 ? want : 148 * 16), n);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    const dim3 grid((unsigned)(want < cap ? want : cap), n);
     switch (ldl / 4) {
       case 1: lik_pass_kernel<1><<<grid, 256, 0, st>>>(a); break;
       case 2: lik_pass_kernel<2><<<grid, 256, 0, st>>>(a); break;
@@ -590,7 +592,8 @@ extern "C" int mmsbm_prod_dist(const int32_t* user, const int32_t* item, int64_t
   MMSBM_REQUIRE(smem <= 227 * 1024, MMSBM_ERANGE, "mmsbm_prod_dist: K*L*R too large for shared memory");
   MMSBM_CUDA(cudaFuncSetAttribute(prod_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t want = (M + 7) / 8;
-  unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  unsigned grid = (unsigned)(want < cap ? want : cap);
   prod_dist_kernel<<<dim3(grid, S), 256, smem, st>>>(a);
   MMSBM_LAUNCH_CHECK("prod_dist_kernel");
   return 0;

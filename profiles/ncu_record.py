@@ -16,7 +16,7 @@ M_F64 = "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"
 M_L2 = "lts__t_sector_hit_rate.pct"
 M_LSU = "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1e-6, "usecond": 1e-3, "msecond": 1.0,
-        "second": 1e3}
+        "second": 1e3, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}          # times in ms, sizes in bytes
 
 
 def main(path, workload, source):
