@@ -105,6 +105,14 @@ int mmsbm_graph_build_side(const int32_t* id_dev, const int32_t* other_dev, cons
                            int32_t* seg_dev, int32_t* adj_dev, int32_t* perm_dev, int32_t* deg_dev,
                            int32_t* sched_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* the work schedule alone, for a contiguous range of segments of an index built over all ids: a rank
+ * of a sharded run can also take SLICES of the full index (seg_dev + lo*R, deg_dev + lo, the whole
+ * adj array: positions in seg are absolute) and build only its own schedule here.
+ * n_ratings = ratings of the range; sched_dev holds mmsbm_sched_elems(n_ratings, n_segments) ints */
+int mmsbm_sched_workspace_bytes(int32_t n_segments, size_t* bytes);
+int mmsbm_sched_build(const int32_t* deg_dev, int32_t n_segments, int64_t n_ratings, int32_t* sched_dev,
+                      void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* ---- a2+a3+a4: one EM iteration for S runs, replaces update_coefficients
  *      (src/kernels_numpy.py:43-79) + normalize_with_d x2 + normalize_with_self
  *      (src/expectation_maximization.py:118-155), i.e. the loop body src/mmsbm.py:244-250 --- */

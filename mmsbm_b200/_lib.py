@@ -39,6 +39,8 @@ _PROTOS = {
     "mmsbm_sched_elems": (C.c_int, [_i64, _i32, C.POINTER(_i64)]),
     "mmsbm_graph_build": (C.c_int, [_vp] * 3 + [_i64, _i32, _i32, _i32] + [_vp] * 10 + [_vp, _sz, _vp]),
     "mmsbm_graph_build_side": (C.c_int, [_vp] * 3 + [_i64, _i32, _i32] + [_vp] * 5 + [_vp, _sz, _vp]),
+    "mmsbm_sched_workspace_bytes": (C.c_int, [_i32, C.POINTER(_sz)]),
+    "mmsbm_sched_build": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _sz, _vp]),
     "mmsbm_nccl_load": (C.c_int, [C.c_char_p]),
     "mmsbm_nccl_unique_id": (C.c_int, [_vp]),
     "mmsbm_nccl_comm_init": (C.c_int, [_vp, _i32, _i32, C.POINTER(_vp)]),

@@ -418,3 +418,26 @@ extern "C" int mmsbm_graph_build_side(const int32_t* id, const int32_t* other, c
   if ((rc = build_one(id, other, level, N, n_ids, R, seg, adj, perm, deg, w, st))) return rc;
   return build_schedule(deg, n_ids, N, sched, w, st);
 }
+
+// The work schedule alone, for a contiguous RANGE of segments of an index that was built over all
+// ids (a rank of a sharded run takes slices of the full index: seg + lo*R, deg + lo, the whole adj
+// array -- positions in seg are absolute -- and only needs its own schedule).  n_ratings = ratings of
+// the range (it sizes the schedule: mmsbm_sched_elems(n_ratings, n_segments)).
+extern "C" int mmsbm_sched_workspace_bytes(int32_t nseg, size_t* bytes) {
+  MMSBM_REQUIRE(bytes && nseg > 0, MMSBM_EINVAL, "mmsbm_sched_workspace_bytes: bad argument");
+  *bytes = 3 * align_up((size_t)nseg * 4) + align_up((size_t)(scan_tiles_for(nseg) + 1) * 4) + 256;
+  return 0;
+}
+extern "C" int mmsbm_sched_build(const int32_t* deg, int32_t nseg, int64_t n_ratings, int32_t* sched, void* ws,
+                                 size_t ws_bytes, void* stream) {
+  MMSBM_REQUIRE(deg && sched && ws && nseg > 0 && n_ratings >= 0, MMSBM_EINVAL, "mmsbm_sched_build: bad argument");
+  size_t need = 0;
+  mmsbm_sched_workspace_bytes(nseg, &need);
+  MMSBM_REQUIRE(ws_bytes >= need, MMSBM_ENOMEM, "mmsbm_sched_build: workspace %zu < %zu", ws_bytes, need);
+  Arena a(ws, ws_bytes);
+  GraphWs w{};
+  w.sa = a.take<int32_t>(nseg); w.sb = a.take<int32_t>(nseg); w.sc = a.take<int32_t>(nseg);
+  w.tile_sums = a.take<int32_t>(scan_tiles_for(nseg) + 1);
+  MMSBM_REQUIRE(w.tile_sums, MMSBM_ENOMEM, "mmsbm_sched_build: workspace carve-up failed");
+  return build_schedule(deg, nseg, n_ratings, sched, w, static_cast<cudaStream_t>(stream));
+}

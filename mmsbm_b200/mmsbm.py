@@ -395,7 +395,12 @@ class MMSBM:
         """k-fold cross-validation; returns the accuracy of every fold and keeps the objects of
         the most accurate one (src/mmsbm.py:371-472).  Under torch.distributed the folds x runs
         jobs shard over the ranks; the result is the same."""
-        pairs = self._make_folds(data, folds)
+        return self._cv_execute(self._make_folds(data, folds))
+
+    def _cv_execute(self, pairs):
+        """Fit / predict / score every (train, test) pair and keep the best fold: the part of
+        ``cv_fit`` after the fold construction (src/mmsbm.py:441-472)."""
+        folds = len(pairs)
         rank, world = dist_info()
         sharded_cv = world > 1 and self.shard == "runs"
         done = {}
@@ -418,10 +423,11 @@ class MMSBM:
         for f, (train, test) in enumerate(pairs):
             self.logger.info(f"Running fold {f + 1} of {folds}...")
             if sharded_cv:
+                # the runs of this fold were fitted on some ranks: only the encoding and a
+                # parameters-only engine (created by predict) are needed here
                 self.data_handler = DataHandler()
-                self._prepare_objects(self.data_handler.format_train_data(train))
+                self._prepare_objects(self.data_handler.format_train_data(train), build_engine=False)
                 self.results = [done[(f, s)] for s in range(self.sampling)]
-                self._resident = None
             else:
                 self.fit(train, silent=True)
             self.prediction_matrix = self.predict(test)

@@ -107,6 +107,15 @@ def shard_rows(data, n_users, n_items, rank, world):
     return rows_u, rows_i, ub, ib
 
 
+def destroy_communicators():
+    """Destroy the cached NCCL communicators of this process (before the process group goes)."""
+    from . import _lib
+    lib = _lib.load()
+    for comm in _COMM_CACHE.values():
+        lib.mmsbm_nccl_comm_destroy(comm)
+    _COMM_CACHE.clear()
+
+
 def _nccl_library_path():
     """The libnccl this process already has mapped (torch's bundled one), so that the library
     binds the same NCCL the process group uses; None lets dlopen search for libnccl.so.2."""
@@ -129,36 +138,54 @@ def _nccl_library_path():
     return None
 
 
+_COMM_CACHE = {}          # (device, rank, world) -> ncclComm_t of this process (created once, kept)
+
+
 class ShardedEngine:
     """S runs sharded over the ranks of the default process group by user range x item range
     (module docstring).  Same surface as ``Engine``: ``set_params`` / ``run`` / ``likelihood`` /
-    ``get_params``; full-size arrays go in and come out on every rank."""
+    ``get_params``; full-size arrays go in and come out on every rank.
+
+    Set-up: every rank uploads the rows once and builds the FULL index on its GPU (one sort per
+    side, a few ms even at 1e8 ratings), derives the two partitions from the device degree
+    vectors, and then works on SLICES of that index: ``seg + lo*R`` and ``deg + lo`` of its own
+    range (positions in ``seg`` are absolute, so ``adj`` is shared) plus a schedule built for the
+    range alone (``mmsbm_sched_build``).  No host-side row shuffling."""
 
     def __init__(self, data, n_users, n_items, n_levels, K, L, device=None):
         from . import _lib
+        from .engine import Engine
         self._lib = _lib
         self.lib = _lib.load(require_device=True)
         self.rank, self.world = dist_info()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
             else torch.device(device)
-        data = np.asarray(data)
-        self.N = int(data.shape[0])
         self.U, self.I, self.R, self.K, self.L = int(n_users), int(n_items), int(n_levels), int(K), int(L)
+        if self.world > min(self.U, self.I):
+            raise ValueError(f"{self.world} ranks for {self.U} users x {self.I} items: every rank needs one of each")
         self.ldk, self.ldl = self.lib.mmsbm_row_stride(self.K), self.lib.mmsbm_row_stride(self.L)
         self.S = 0
         self._exchange = None
         self._peers = []
         self._comm = None
-        rows_u, rows_i, self.ub, self.ib = shard_rows(data, self.U, self.I, self.rank, self.world)
-        self.ulo, self.uhi = int(self.ub[self.rank]), int(self.ub[self.rank + 1])
-        self.ilo, self.ihi = int(self.ib[self.rank]), int(self.ib[self.rank + 1])
-        self.Uo, self.Io = self.uhi - self.ulo, self.ihi - self.ilo
-        self.Nu, self.Ni = int(rows_u.shape[0]), int(rows_i.shape[0])
+        self._ptrs = None
+        base = Engine(data, self.U, self.I, self.R, self.K, self.L, device=self.device)   # the full index
+        self._base = base
+        self.N = base.N
+        R = self.R
         with torch.cuda.device(self.device):
-            self.useg, self.uadj, self.udeg, self.usched = self._build_side(
-                rows_u, self.Uo, self.I, id_col=0)
-            self.iseg, self.iadj, self.ideg, self.isched = self._build_side(
-                rows_i, self.U, self.Io, id_col=1)
+            self.ub = balanced_partition(base.udeg[:self.U].cpu().numpy(), self.world)
+            self.ib = balanced_partition(base.ideg[:self.I].cpu().numpy(), self.world)
+            self.ulo, self.uhi = int(self.ub[self.rank]), int(self.ub[self.rank + 1])
+            self.ilo, self.ihi = int(self.ib[self.rank]), int(self.ib[self.rank + 1])
+            self.Uo, self.Io = self.uhi - self.ulo, self.ihi - self.ilo
+            ends = torch.stack([base.useg[self.ulo * R], base.useg[self.uhi * R],
+                                base.iseg[self.ilo * R], base.iseg[self.ihi * R]]).cpu().numpy()
+            self.Nu, self.Ni = int(ends[1] - ends[0]), int(ends[3] - ends[2])
+            self.useg, self.uadj, self.udeg = base.useg[self.ulo * R:], base.uadj, base.udeg[self.ulo:]
+            self.iseg, self.iadj, self.ideg = base.iseg[self.ilo * R:], base.iadj, base.ideg[self.ilo:]
+            self.usched = self._build_sched(self.udeg, self.Uo, self.Nu)
+            self.isched = self._build_sched(self.ideg, self.Io, self.Ni)
             if self.world > 1:
                 self._open_nccl()
 
@@ -166,42 +193,26 @@ class ShardedEngine:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def _build_side(self, rows, n_u, n_i, id_col):
-        """Index of one side from int64 rows whose column ``id_col`` is the (shifted) segment id."""
+    def _build_sched(self, deg, n_seg, n_ratings):
         lib, _lib = self.lib, self._lib
-        i32 = torch.int32
-        n = int(rows.shape[0])
-        n_ids = n_u if id_col == 0 else n_i
-        raw = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.int64)).to(self.device)
-        cols = torch.empty((3, max(n, 1)), dtype=i32, device=self.device)
-        bad = torch.zeros(1, dtype=i32, device=self.device)
-        _lib.check(lib.mmsbm_split_triples(raw.data_ptr(), n, n_u, n_i, self.R, cols[0].data_ptr(),
-                                           cols[1].data_ptr(), cols[2].data_ptr(), bad.data_ptr(),
-                                           self._stream()), "split_triples")
-        if int(bad.item()):
-            raise ValueError("data holds an id outside [0,U) x [0,I) x [0,R)")
-        del raw
-        seg = torch.empty(n_ids * self.R + 1, dtype=i32, device=self.device)
-        adj = torch.empty(max(n, 1), dtype=i32, device=self.device)
-        perm = torch.empty(max(n, 1), dtype=i32, device=self.device)
-        deg = torch.empty(n_ids, dtype=i32, device=self.device)
-        ne = C.c_int64(0)
-        _lib.check(lib.mmsbm_sched_elems(n, n_ids, C.byref(ne)), "sched_elems")
-        sched = torch.empty(ne.value, dtype=i32, device=self.device)
-        need = C.c_size_t(0)
-        _lib.check(lib.mmsbm_graph_workspace_bytes(n, n_ids, n_ids, self.R, C.byref(need)),
-                   "graph_workspace_bytes")
+        ne, need = C.c_int64(0), C.c_size_t(0)
+        _lib.check(lib.mmsbm_sched_elems(n_ratings, n_seg, C.byref(ne)), "sched_elems")
+        _lib.check(lib.mmsbm_sched_workspace_bytes(n_seg, C.byref(need)), "sched_workspace_bytes")
+        sched = torch.empty(ne.value, dtype=torch.int32, device=self.device)
         ws = torch.empty(max(need.value, 16), dtype=torch.uint8, device=self.device)
-        ids, other = (cols[0], cols[1]) if id_col == 0 else (cols[1], cols[0])
-        _lib.check(lib.mmsbm_graph_build_side(ids.data_ptr(), other.data_ptr(), cols[2].data_ptr(), n, n_ids,
-                                              self.R, seg.data_ptr(), adj.data_ptr(), perm.data_ptr(),
-                                              deg.data_ptr(), sched.data_ptr(), ws.data_ptr(), need.value,
-                                              self._stream()), "graph_build_side")
+        _lib.check(lib.mmsbm_sched_build(deg.data_ptr(), n_seg, n_ratings, sched.data_ptr(), ws.data_ptr(),
+                                         need.value, self._stream()), "sched_build")
         torch.cuda.current_stream(self.device).synchronize()
-        return seg, adj, deg, sched
+        return sched
 
     def _open_nccl(self):
+        """One communicator per process and group shape, created on first use and kept (creating
+        one costs about a second; engines come and go)."""
         lib, _lib = self.lib, self._lib
+        key = (self.device.index, self.rank, self.world)
+        if key in _COMM_CACHE:
+            self._comm = _COMM_CACHE[key]
+            return
         path = _nccl_library_path()
         _lib.check(lib.mmsbm_nccl_load(path.encode() if path else None), "nccl_load")
         uid = (C.c_ubyte * 128)()
@@ -212,7 +223,7 @@ class ShardedEngine:
         uid = (C.c_ubyte * 128).from_buffer_copy(box[0])
         comm = C.c_void_p()
         _lib.check(lib.mmsbm_nccl_comm_init(uid, self.rank, self.world, C.byref(comm)), "nccl_comm_init")
-        self._comm = comm
+        self._comm = _COMM_CACHE[key] = comm
 
     def _open_exchange(self, S):
         lib, _lib = self.lib, self._lib
@@ -259,10 +270,10 @@ class ShardedEngine:
             self._exchange = None
 
     def close(self):
+        """Release the exchange buffer (collective).  The communicator stays cached for the next
+        engine of this process; ``destroy_communicators`` releases it."""
         self.close_exchange()
-        if self._comm is not None:
-            self.lib.mmsbm_nccl_comm_destroy(self._comm)
-            self._comm = None
+        self._comm = None
 
     def _shard(self):
         s = self._lib.Shard()

@@ -23,7 +23,7 @@ fi
 for f in gpurun_out/${TAG}_bench_*_n$N.json; do python - "$f" <<'PY'
 import json, sys
 try:
-    d = json.load(open(sys.argv[1]))
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 except Exception as e:
     print(sys.argv[1], "unreadable", e); raise SystemExit
 print(sys.argv[1], "value %.3e" % d["value"], "ms/step %.2f" % d["ms_per_step"], d["config"].get("mode"), d["config"].get("parallelism", "")[:60])
@@ -32,6 +32,6 @@ for m, r in (d.get("modes") or {}).items():
 nf = d.get("netflix_ratings_sharded")
 if nf: print("    netflix %.3e" % nf["value"], "ms/it %.4f" % nf["ms_per_iteration"], "wait", nf["exchange_wait_ms_per_iteration"], "lik diff", nf.get("likelihood_rel_diff_vs_one_gpu"))
 if d.get("e2e"): print("    e2e %.3e" % d["e2e"]["value"], "ms/step %.1f" % d["e2e"]["ms_per_step"])
-if "cv_accuracies" in d: print("    cv", d["cv_accuracies"], d["wall_s_per_cv_fit"], d["config"]["parallelism"])
+if "cv_accuracies" in d: print("    cv", d["cv_accuracies"], d["wall_s_per_cv"], d["config"]["parallelism"])
 PY
 done

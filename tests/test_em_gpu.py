@@ -702,3 +702,56 @@ def test_sharded_engine_with_one_rank_equals_engine(K, L, S):
     ms = b.run(2, prof=True)
     assert ms[0] > 0.0
     b.close()
+
+
+def test_one_sided_build_equals_a_slice_of_the_full_index():
+    """mmsbm_graph_build_side on the rows of a user range (what a caller that pre-partitions its
+    ratings would use) == the slice of the full index a ShardedEngine rank works on, and
+    mmsbm_sched_build on the degree slice == the schedule the one-sided build makes."""
+    import ctypes as C
+    import torch
+    from mmsbm_b200 import _lib
+    from mmsbm_b200.engine import Engine
+    lib = _lib.load(require_device=True)
+    N, U, I, R = 90000, 500, 300, 5
+    data = random_triples(97, N, U, I, R, heavy_tail=True)       # user 0 holds > 2048 ratings: pieces
+    full = Engine(data, U, I, R, 4, 4)
+    lo, hi = 0, 140
+    rows = data[(data[:, 0] >= lo) & (data[:, 0] < hi)].copy()
+    rows[:, 0] -= lo
+    n, n_ids = len(rows), hi - lo
+    dev, i32 = full.device, torch.int32
+    cols = [torch.from_numpy(np.ascontiguousarray(rows[:, c], dtype=np.int32)).to(dev) for c in range(3)]
+    seg = torch.empty(n_ids * R + 1, dtype=i32, device=dev)
+    adj, perm = torch.empty(n, dtype=i32, device=dev), torch.empty(n, dtype=i32, device=dev)
+    deg = torch.empty(n_ids, dtype=i32, device=dev)
+    ne, need = C.c_int64(0), C.c_size_t(0)
+    _lib.check(lib.mmsbm_sched_elems(n, n_ids, C.byref(ne)), "sched_elems")
+    sched = torch.zeros(ne.value, dtype=i32, device=dev)
+    _lib.check(lib.mmsbm_graph_workspace_bytes(n, n_ids, n_ids, R, C.byref(need)), "graph_workspace_bytes")
+    ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.mmsbm_graph_build_side(cols[0].data_ptr(), cols[1].data_ptr(), cols[2].data_ptr(), n, n_ids, R,
+                                          seg.data_ptr(), adj.data_ptr(), perm.data_ptr(), deg.data_ptr(),
+                                          sched.data_ptr(), ws.data_ptr(), need.value, st), "graph_build_side")
+    torch.cuda.synchronize()
+    fseg = full.useg.cpu().numpy()
+    base = fseg[lo * R]
+    np.testing.assert_array_equal(seg.cpu().numpy(), fseg[lo * R:hi * R + 1] - base)
+    np.testing.assert_array_equal(adj.cpu().numpy(), full.uadj.cpu().numpy()[base:fseg[hi * R]])
+    np.testing.assert_array_equal(deg.cpu().numpy(), full.udeg.cpu().numpy()[lo:hi])
+    assert n == fseg[hi * R] - base
+    _lib.check(lib.mmsbm_sched_workspace_bytes(n_ids, C.byref(need)), "sched_workspace_bytes")
+    ws2 = torch.empty(need.value, dtype=torch.uint8, device=dev)
+    sched2 = torch.zeros(ne.value, dtype=i32, device=dev)
+    _lib.check(lib.mmsbm_sched_build(full.udeg[lo:].data_ptr(), n_ids, n, sched2.data_ptr(), ws2.data_ptr(),
+                                     need.value, st), "sched_build")
+    torch.cuda.synchronize()
+    a, b = sched.cpu().numpy(), sched2.cpu().numpy()
+    assert a[0] > n_ids and a[2] >= 1                        # more pieces than segments: a long one exists
+    pmax = n_ids + n // 2048 + 1
+    lmax = n // 2048 + 1
+    np.testing.assert_array_equal(a[:4], b[:4])
+    for off, cnt in ((4, a[0]), (4 + pmax, a[0]), (4 + 2 * pmax, a[0]), (4 + 3 * pmax, a[2]),
+                     (4 + 3 * pmax + lmax, a[2] + 1)):       # the filled part of each table
+        np.testing.assert_array_equal(a[off:off + cnt], b[off:off + cnt])
