@@ -34,11 +34,14 @@ def shard_runs(n_runs, rank, world):
 
 
 def shard_jobs(n_folds, n_runs, rank, world):
-    """(fold, run) jobs of ``rank`` for cv_fit: the folds x runs grid in fold-major order dealt
-    round-robin, so the jobs of a rank differ by at most one (src/mmsbm.py:420-457 runs them
-    serially)."""
+    """(fold, run) jobs of ``rank`` for cv_fit: the folds x runs grid in fold-major order cut into
+    ``world`` contiguous blocks whose sizes differ by at most one (src/mmsbm.py:420-457 runs the
+    jobs serially).  Contiguous blocks keep the runs of a fold together: a rank encodes and
+    indexes as few folds as possible and batches their runs in one launch."""
     jobs = [(f, s) for f in range(n_folds) for s in range(n_runs)]
-    return jobs[rank::world]
+    base, extra = divmod(len(jobs), world)
+    lo = rank * base + min(rank, extra)
+    return jobs[lo:lo + base + (1 if rank < extra else 0)]
 
 
 def gather_runs(local, n_runs):
