@@ -595,11 +595,13 @@ def sharded_record(cx, data, shape, T, steps, warmup, check_single_gpu):
     total_it = (steps + warmup) * T + min(T, 20) // 2 * 2
     rec = {"value": float(N) * T * S * steps / (ms * 1e-3), "unit": "rating-updates/s",
            "ms_per_iteration": ms / steps / T, "ms_per_step": ms / steps,
-           "exchange_wait_ms_per_iteration": cx.max_over_ranks(prof[1]),
-           "iteration_ms_when_profiled": cx.max_over_ranks(prof[0]),
+           "pr_wait_ms_per_iteration": cx.max_over_ranks(prof[1]),
+           "stage_ms_when_profiled": dict(zip(("iteration", "wait_n_pr", "p_tables_w", "pass_1", "n_publish_pr_1",
+                                               "pass_2", "n_publish_2"), [cx.max_over_ranks(x) for x in prof[:7]])),
            "exchange": "theta / eta rows: copy-engine DMA into every peer's exchange buffer (CUDA IPC over "
-                       "NVLink), overlapped with the by-item pass; one ncclAllReduce of n_pr "
-                       f"({S * K * L * R * 8} bytes) per iteration, which is also the barrier",
+                       "NVLink, one copy stream per peer), overlapped with the other pass (the passes alternate "
+                       f"their order); one ncclAllReduce of n_pr ({S * K * L * R * 8} bytes) and two one-element "
+                       "arrival barriers per iteration on a side stream",
            "exchange_bytes_out_per_iteration": int((sh.Uo * sh.ldk + sh.Io * sh.ldl) * 8 * S * (cx.world - 1)),
            "local_ratings": [int(sh.Nu), int(sh.Ni)], "setup_s": setup_s, "gpu_launches_per_rank": int(launches),
            "likelihood_run0": float(lik[0]), "iterations_run": total_it}

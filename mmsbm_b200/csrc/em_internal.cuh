@@ -10,6 +10,8 @@ constexpr int kPrSlabs = 128;
 
 int env_int(const char* name, int dflt);
 int sm_count();                       // multiprocessors of the current device (cached per device)
+// resident CTA slots the persistent segment pass leaves free (for NCCL kernels of a sharded run)
+void set_reserved_ctas(int n);
 
 // How the S runs of a launch row are served by the segment pass for neighbour rows of NBp
 // doubles: runs [0, 6*hexas) six per warp, then `pairs` pairs (pair groups numbered over ALL

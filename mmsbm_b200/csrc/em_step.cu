@@ -543,9 +543,14 @@ static bool pairs_enabled(int NBp, int n_runs) {
 // grid.x of a segment pass.  The piece count lives on the device, so the grid is sized for its upper
 // bound (warps past it exit).  With launch-wide claiming (a.counters) the CTAs are persistent: as
 // many as stay resident (148 SMs x CTAs per SM), one starting piece per warp at least.
+static int g_reserved_ctas = 0;
+void set_reserved_ctas(int n) { g_reserved_ctas = n > 0 ? n : 0; }
+
 static unsigned grid_x_for(const SegArgs& a, int ctas_per_sm) {
   if (!a.counters) return (unsigned)((a.pmax + a.segs_per_cta - 1) / a.segs_per_cta);
-  const int64_t want = (a.pmax + kWarps - 1) / kWarps, resident = (int64_t)sm_count() * ctas_per_sm;
+  int64_t resident = (int64_t)sm_count() * ctas_per_sm - g_reserved_ctas;
+  if (resident < 1) resident = 1;
+  const int64_t want = (a.pmax + kWarps - 1) / kWarps;
   return (unsigned)(want < resident ? want : resident);
 }
 

@@ -94,16 +94,50 @@ static const double* table_ptr(const void* base, const GridLayout& g, int half, 
   return reinterpret_cast<const double*>(static_cast<const char*>(base) + (size_t)half * g.half_bytes + t.off);
 }
 
-struct PushStreams {
-  cudaStream_t cs = nullptr;
-  cudaEvent_t ready = nullptr, pushed = nullptr;
+// Streams and events of the exchange: one COPY stream per peer (the pushes to different peers run
+// on different copy engines at the same time; on one stream they would queue up behind each other
+// and a 30 MB push made of 21 strided copies would be latency-bound), one SIDE stream for NCCL.
+struct Exchange {
+  int peers = 0;
+  cudaStream_t side = nullptr;
+  cudaStream_t cp[16] = {nullptr};
+  cudaEvent_t ready = nullptr;                  // main -> copy streams: the slice is in the own tables
+  cudaEvent_t done[16] = {nullptr};             // copy stream p -> side: its copies have been issued and finished
+  cudaEvent_t partial = nullptr, pr_done = nullptr;      // main -> side, side -> main: n_pr all-reduce
+  // side -> main: [0][.] theta tables, [1][.] eta tables complete everywhere; two events per table,
+  // used by alternate iterations (a pass waits for the PREVIOUS iteration's barrier while this
+  // iteration's one is already being recorded)
+  cudaEvent_t arrived[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  int open(int world) {
+    peers = world - 1;
+    if (peers <= 0) return 0;
+    MMSBM_REQUIRE(peers <= 16, MMSBM_ERANGE, "sharded runs support up to 17 ranks");
+    MMSBM_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    for (int p = 0; p < peers; ++p) {
+      MMSBM_CUDA(cudaStreamCreateWithFlags(&cp[p], cudaStreamNonBlocking));
+      MMSBM_CUDA(cudaEventCreateWithFlags(&done[p], cudaEventDisableTiming));
+    }
+    cudaEvent_t* evs[] = {&ready, &partial, &pr_done, &arrived[0][0], &arrived[0][1], &arrived[1][0], &arrived[1][1]};
+    for (cudaEvent_t* e : evs) MMSBM_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    return 0;
+  }
+  ~Exchange() {                                 // queued work finishes first: handles are released lazily
+    cudaEvent_t evs[] = {ready, partial, pr_done, arrived[0][0], arrived[0][1], arrived[1][0], arrived[1][1]};
+    for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    for (int p = 0; p < peers; ++p) {
+      if (done[p]) cudaEventDestroy(done[p]);
+      if (cp[p]) cudaStreamDestroy(cp[p]);
+    }
+    if (side) cudaStreamDestroy(side);
+  }
 };
 
 // own rows [lo, lo + n_own) of one parameter (plain [S][n_own][ld]) -> the tables of half `half`:
-// interleave into the own buffer on `st`, then DMA the slice into every peer's buffer on `cs`
+// interleave into the own buffer on `st`, then DMA the slice into every peer's buffer, one copy
+// stream per peer (barrier_on_side makes the side stream wait for them)
 static int publish_side(const mmsbm_shard_t& sh, const GridLayout& g, const Table* tabs, int n_tabs,
                         const double* own_rows, int n_own, int lo, int half, cudaStream_t st,
-                        const PushStreams& ps) {
+                        const Exchange& ex) {
   char* mine = static_cast<char*>(sh.exchange_dev[sh.rank]);
   for (int k = 0; k < n_tabs; ++k) {
     const Table& t = tabs[k];
@@ -113,11 +147,12 @@ static int publish_side(const mmsbm_shard_t& sh, const GridLayout& g, const Tabl
     if (rc) return rc;
   }
   if (sh.world == 1) return 0;
-  MMSBM_CUDA(cudaEventRecord(ps.ready, st));
-  MMSBM_CUDA(cudaStreamWaitEvent(ps.cs, ps.ready, 0));
+  MMSBM_CUDA(cudaEventRecord(ex.ready, st));
   for (int d = 1; d < sh.world; ++d) {
-    const int peer = (sh.rank + d) % sh.world;               // staggered: no two ranks start on one peer
+    const int peer = (sh.rank + d) % sh.world;               // copy stream d-1 serves peer rank+d
+    cudaStream_t cs = ex.cp[d - 1];
     char* theirs = static_cast<char*>(sh.exchange_dev[peer]);
+    MMSBM_CUDA(cudaStreamWaitEvent(cs, ex.ready, 0));
     for (int k = 0; k < n_tabs; ++k) {
       const Table& t = tabs[k];
       if (t.groups == 0) continue;
@@ -125,9 +160,20 @@ static int publish_side(const mmsbm_shard_t& sh, const GridLayout& g, const Tabl
       const size_t pitch = (size_t)t.n_all * row_bytes;
       const size_t o = (size_t)half * g.half_bytes + t.off + ((size_t)t.group0 * t.n_all + lo) * row_bytes;
       MMSBM_CUDA(cudaMemcpy2DAsync(theirs + o, pitch, mine + o, pitch, (size_t)n_own * row_bytes,
-                                   (size_t)t.groups, cudaMemcpyDeviceToDevice, ps.cs));
+                                   (size_t)t.groups, cudaMemcpyDeviceToDevice, cs));
     }
+    MMSBM_CUDA(cudaEventRecord(ex.done[d - 1], cs));
   }
+  return 0;
+}
+
+// on the side stream, after this rank's pushes: a one-element all-reduce = "every rank's slices of
+// this table have landed everywhere, and every rank is past the pass that produced them"
+static int barrier_on_side(const mmsbm_shard_t& sh, const GridLayout& g, const Exchange& ex, cudaEvent_t signal) {
+  for (int p = 0; p < ex.peers; ++p) MMSBM_CUDA(cudaStreamWaitEvent(ex.side, ex.done[p], 0));
+  double* scratch = reinterpret_cast<double*>(static_cast<char*>(sh.exchange_dev[sh.rank]) + 2 * g.half_bytes);
+  MMSBM_NCCL(g_nccl.AllReduce(scratch, scratch, 1, ncclFloat64, ncclSum, static_cast<ncclComm_t>(sh.nccl_comm), ex.side));
+  MMSBM_CUDA(cudaEventRecord(signal, ex.side));
   return 0;
 }
 
@@ -168,7 +214,8 @@ static ShardDims shard_dims(const mmsbm_shard_t& s) {
   d.p_elems = (size_t)S * d.ldk * d.ldl * R;
   d.wg_u = (size_t)S * s.n_users_own * d.rnb_u;
   d.wg_i = (size_t)S * s.n_items_own * d.rnb_i;
-  d.partial = (size_t)S * kPrSlabs * (d.emit_items ? s.L * R * d.ldk : s.K * R * d.ldl);
+  const size_t pi = (size_t)s.L * R * d.ldk, pu = (size_t)s.K * R * d.ldl;   // either side may emit n_pr
+  d.partial = (size_t)S * kPrSlabs * (pi > pu ? pi : pu);
   d.slots_u = (size_t)S * d.smax_u * d.rnb_u;
   d.slots_i = (size_t)S * d.smax_i * d.rnb_i;
   d.ctr = 2 * ((size_t)S + 8);
@@ -285,31 +332,21 @@ extern "C" int mmsbm_shard_publish(const mmsbm_shard_t* sh, const double* theta_
   int rc = check_shard(sh, "mmsbm_shard_publish");
   if (rc) return rc;
   MMSBM_REQUIRE(theta_own && eta_own && (half == 0 || half == 1), MMSBM_EINVAL, "mmsbm_shard_publish: bad argument");
+  if (sh->world > 1 && (rc = nccl_ready())) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const GridLayout g = grid_layout(sh->n_users, sh->n_items, sh->K, sh->L, sh->n_runs);
-  PushStreams ps;
-  struct Cleanup {
-    PushStreams& p;
-    ~Cleanup() {
-      if (p.ready) cudaEventDestroy(p.ready);
-      if (p.pushed) cudaEventDestroy(p.pushed);
-      if (p.cs) cudaStreamDestroy(p.cs);
-    }
-  } cleanup{ps};
-  if (sh->world > 1) {
-    MMSBM_CUDA(cudaStreamCreateWithFlags(&ps.cs, cudaStreamNonBlocking));
-    MMSBM_CUDA(cudaEventCreateWithFlags(&ps.ready, cudaEventDisableTiming));
-    MMSBM_CUDA(cudaEventCreateWithFlags(&ps.pushed, cudaEventDisableTiming));
+  Exchange ex;
+  if ((rc = ex.open(sh->world))) return rc;
+  if (sh->world > 1) {                          // the side stream starts behind everything queued on `st`
+    MMSBM_CUDA(cudaEventRecord(ex.partial, st));
+    MMSBM_CUDA(cudaStreamWaitEvent(ex.side, ex.partial, 0));
   }
-  if ((rc = publish_side(*sh, g, g.theta, 2, theta_own, sh->n_users_own, sh->user_lo, half, st, ps))) return rc;
-  if ((rc = publish_side(*sh, g, g.eta, 3, eta_own, sh->n_items_own, sh->item_lo, half, st, ps))) return rc;
+  if ((rc = publish_side(*sh, g, g.theta, 2, theta_own, sh->n_users_own, sh->user_lo, half, st, ex))) return rc;
+  if ((rc = publish_side(*sh, g, g.eta, 3, eta_own, sh->n_items_own, sh->item_lo, half, st, ex))) return rc;
   if (sh->world > 1) {
-    if ((rc = nccl_ready())) return rc;
-    MMSBM_CUDA(cudaEventRecord(ps.pushed, ps.cs));
-    MMSBM_CUDA(cudaStreamWaitEvent(st, ps.pushed, 0));
-    double* scratch = reinterpret_cast<double*>(static_cast<char*>(sh->exchange_dev[sh->rank]) + 2 * g.half_bytes);
-    MMSBM_CUDA(cudaMemsetAsync(scratch, 0, 8, st));
-    MMSBM_NCCL(g_nccl.AllReduce(scratch, scratch, 1, ncclFloat64, ncclSum, static_cast<ncclComm_t>(sh->nccl_comm), st));
+    // (one barrier covers both tables: the copy streams run their theta and eta copies in order)
+    if ((rc = barrier_on_side(*sh, g, ex, ex.arrived[0][0]))) return rc;
+    MMSBM_CUDA(cudaStreamWaitEvent(st, ex.arrived[0][0], 0));
   }
   return 0;
 }
@@ -318,8 +355,26 @@ extern "C" int mmsbm_shard_publish(const mmsbm_shard_t* sh, const double* theta_
 // [S][n_users_own][ldk] / [S][n_items_own][ldl]; pr_a/_b: [S][K][L][R], replicated.  The tables of half
 // `half` must hold the parameters of the _a buffers on every rank (mmsbm_shard_publish).  The result is
 // in _a (tables in `half`) when iterations is even, else in _b (tables in half ^ 1).
-// prof (optional, 2 floats): mean device ms per iteration, and of it the mean ms between the end of the
-// rank's compute and the end of the n_pr all-reduce (exposed exchange + barrier); synchronises.
+//
+// Schedule of one iteration with peers (main stream st, side stream for NCCL, one copy stream per peer):
+//   st:   P tables, W of the own users and items
+//   st:   wait "tables of pass 1 arrived" | pass 1 | n of its side | interleave the new rows into the own
+//         next tables | n_pr partial from the g rows of pass 1
+//   copy: push the slice to every peer (overlaps pass 2)      side: all-reduce n_pr (overlaps pass 2),
+//                                                                   then, once the pushes are done, the
+//                                                                   arrival barrier of that table
+//   st:   wait "tables of pass 2 arrived" | pass 2 | n | interleave      copy: push      side: barrier
+//   st:   wait n_pr | normalise pr
+// Passes ALTERNATE their order from one iteration to the next (by-user, by-item | by-item, by-user | ...):
+// the table a first pass gathers was pushed during the previous iteration's second pass, and the one a
+// second pass gathers was pushed at the very end of the previous iteration and has the whole first pass to
+// arrive, so no push and no barrier is waited for.  n_pr is emitted by the side of pass 1 so that its
+// all-reduce hides behind pass 2.  With world == 1 nothing of this applies: fixed order, n_pr from the side
+// with fewer segments and normalised in place -- bit for bit what mmsbm_em_run computes.
+//
+// prof (optional, 8 floats): mean device ms per iteration of {whole iteration, wait for n_pr at its end,
+// P tables + W, pass 1, n + publish + pr partial, (wait +) pass 2, n + publish, unused}; measuring
+// synchronises every iteration (which serialises the overlap: stage times, not a throughput figure).
 extern "C" int mmsbm_em_run_sharded(const mmsbm_shard_t* shp, int32_t iterations, double* theta_a, double* eta_a,
                                     double* pr_a, double* theta_b, double* eta_b, double* pr_b, int32_t half,
                                     void* ws, size_t ws_bytes, void* stream, float* prof) {
@@ -331,7 +386,8 @@ extern "C" int mmsbm_em_run_sharded(const mmsbm_shard_t* shp, int32_t iterations
   MMSBM_REQUIRE(sh.useg_dev && sh.udeg_dev && sh.usched_dev && sh.iseg_dev && sh.ideg_dev && sh.isched_dev &&
                     (sh.n_ratings_u == 0 || sh.uadj_dev) && (sh.n_ratings_i == 0 || sh.iadj_dev), MMSBM_EINVAL,
                 "mmsbm_em_run_sharded: null index pointer");
-  if (sh.world > 1 && (rc = nccl_ready())) return rc;
+  const bool peers = sh.world > 1;
+  if (peers && (rc = nccl_ready())) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int S = sh.n_runs, R = sh.n_levels, K = sh.K, L = sh.L;
   const int Uo = sh.n_users_own, Io = sh.n_items_own;
@@ -351,29 +407,33 @@ extern "C" int mmsbm_em_run_sharded(const mmsbm_shard_t* shp, int32_t iterations
   MMSBM_REQUIRE(pw_u && pn_u && pw_i && pn_i && wg_u && wg_i && partial && slots_u && slots_i && counters,
                 MMSBM_ENOMEM, "mmsbm_em_run_sharded: workspace too small (%zu)", ws_bytes);
 
-  PushStreams ps;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // profiling: start, compute done, exchange done, end
+  Exchange ex;
+  if ((rc = ex.open(sh.world))) return rc;
+  constexpr int kProf = 7;
+  cudaEvent_t ev[kProf] = {nullptr};
   struct Cleanup {
-    PushStreams& p;
     cudaEvent_t* ev;
     ~Cleanup() {
-      if (p.ready) cudaEventDestroy(p.ready);
-      if (p.pushed) cudaEventDestroy(p.pushed);
-      if (p.cs) cudaStreamDestroy(p.cs);
-      for (int k = 0; k < 4; ++k) if (ev[k]) cudaEventDestroy(ev[k]);
+      for (int k = 0; k < kProf; ++k) if (ev[k]) cudaEventDestroy(ev[k]);
+      set_reserved_ctas(0);
     }
-  } cleanup{ps, ev};
-  if (sh.world > 1) {
-    MMSBM_CUDA(cudaStreamCreateWithFlags(&ps.cs, cudaStreamNonBlocking));
-    MMSBM_CUDA(cudaEventCreateWithFlags(&ps.ready, cudaEventDisableTiming));
-    MMSBM_CUDA(cudaEventCreateWithFlags(&ps.pushed, cudaEventDisableTiming));
-  }
-  if (prof) for (int k = 0; k < 4; ++k) MMSBM_CUDA(cudaEventCreate(&ev[k]));
-  double prof_iter = 0.0, prof_exch = 0.0;
+  } cleanup{ev};
+  if (prof) for (int k = 0; k < kProf; ++k) MMSBM_CUDA(cudaEventCreate(&ev[k]));
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define MMSBM_MARK(k) do { if (prof) MMSBM_CUDA(cudaEventRecord(ev[k], st)); } while (0)
 
   const int64_t n_big = sh.n_ratings_u > sh.n_ratings_i ? sh.n_ratings_u : sh.n_ratings_i;
   const bool dyn = env_int("MMSBM_DYN", n_big >= ((int64_t)1 << 22) ? 1 : 0) != 0;
+  const bool alternate = peers && env_int("MMSBM_SHARD_ALTERNATE", 1) != 0;
+  // persistent CTAs of the passes leave a few slots free so that the NCCL kernels of the side stream
+  // can start while a pass runs
+  if (peers) set_reserved_ctas(env_int("MMSBM_SHARD_RESERVE", 4));
   const void* mine = sh.exchange_dev[sh.rank];
+  if (peers) {                                  // the side stream starts behind everything queued on `st`
+    MMSBM_CUDA(cudaEventRecord(ex.partial, st));
+    MMSBM_CUDA(cudaStreamWaitEvent(ex.side, ex.partial, 0));
+  }
+  bool have_arrival[2] = {false, false};        // an arrival barrier of this call is pending for [theta, eta]
 
   for (int it = 0; it < iterations; ++it) {
     const bool fwd = (it & 1) == 0;
@@ -381,55 +441,99 @@ extern "C" int mmsbm_em_run_sharded(const mmsbm_shard_t* shp, int32_t iterations
     const double* th = fwd ? theta_a : theta_b; const double* et = fwd ? eta_a : eta_b;
     const double* pr = fwd ? pr_a : pr_b;
     double* th_n = fwd ? theta_b : theta_a; double* et_n = fwd ? eta_b : eta_a; double* pr_n = fwd ? pr_b : pr_a;
-    if (prof) MMSBM_CUDA(cudaEventRecord(ev[0], st));
+    const bool users_first = !alternate || (it & 1) == 0;
+    // n_pr comes from the g rows of ONE side: of pass 1 with peers, of the side with fewer segments alone
+    const bool emit_items = alternate ? !users_first : d.emit_items;
+
+    auto pass_users = [&]() -> int {            // gathers eta rows of ALL items, new theta rows of the own users
+      if (have_arrival[1]) MMSBM_CUDA(cudaStreamWaitEvent(st, ex.arrived[1][(it + 1) & 1], 0));
+      SegArgs a{sh.useg_dev, sh.uadj_dev, sh.usched_dev, table_ptr(mine, g, cur, g.eta[2]), wg_u, slots_u, d.pmax_u,
+                d.lmax_u, d.smax_u, Uo, sh.n_items, d.ldl, R, 0, 0, 0, dyn ? counters : nullptr};
+      return launch_segment_pass_and_fixup(a, table_ptr(mine, g, cur, g.eta[1]), table_ptr(mine, g, cur, g.eta[0]),
+                                           sh.n_ratings_u, S, st);
+    };
+    auto finish_users = [&]() -> int {
+      int r = launch_n(wg_u, pn_u, th, sh.udeg_dev, th_n, Uo, d.ldk, d.rnb_u, 1, S, st);
+      if (r) return r;
+      if ((r = publish_side(sh, g, g.theta, 2, th_n, Uo, sh.user_lo, nxt, st, ex))) return r;
+      return 0;
+    };
+    auto pass_items = [&]() -> int {            // gathers theta rows of ALL users, new eta rows of the own items
+      if (have_arrival[0]) MMSBM_CUDA(cudaStreamWaitEvent(st, ex.arrived[0][(it + 1) & 1], 0));
+      SegArgs a{sh.iseg_dev, sh.iadj_dev, sh.isched_dev, table_ptr(mine, g, cur, g.theta[1]), wg_i, slots_i, d.pmax_i,
+                d.lmax_i, d.smax_i, Io, sh.n_users, d.ldk, R, 0, 0, 0, dyn ? counters + d.ctr / 2 : nullptr};
+      return launch_segment_pass_and_fixup(a, table_ptr(mine, g, cur, g.theta[0]), nullptr, sh.n_ratings_i, S, st);
+    };
+    auto finish_items = [&]() -> int {
+      int r = launch_n(wg_i, pn_i, et, sh.ideg_dev, et_n, Io, d.ldl, d.rnb_i, 1, S, st);
+      if (r) return r;
+      return publish_side(sh, g, g.eta, 3, et_n, Io, sh.item_lo, nxt, st, ex);
+    };
+    auto emit_pr = [&]() -> int {               // partial n_pr over the own segments of the emitting side
+      return launch_pr(emit_items ? et : th, emit_items ? wg_i : wg_u, partial, pr, pr_n, emit_items ? Io : Uo,
+                       emit_items ? L : K, emit_items ? d.ldl : d.ldk, emit_items ? d.ldk : d.ldl, K, L, R, S,
+                       emit_items, !peers, st);
+    };
+    auto after_publish = [&](int which) -> int {   // side stream: [n_pr all-reduce,] arrival barrier of table `which`
+      if (!peers) return 0;
+      return barrier_on_side(sh, g, ex, ex.arrived[which][it & 1]);
+    };
+
+    MMSBM_MARK(0);
     if (dyn) MMSBM_CUDA(cudaMemsetAsync(counters, 0, d.ctr * 4, st));
     if ((rc = launch_prep_p(pr, K, L, R, d.ldk, d.ldl, S, pw_u, pn_u, pw_i, pn_i, st))) return rc;
     if ((rc = launch_w(th, pw_u, wg_u, Uo, d.ldk, d.rnb_u, S, st))) return rc;
     if ((rc = launch_w(et, pw_i, wg_i, Io, d.ldl, d.rnb_i, S, st))) return rc;
-    // ---- by-user pass over the own users: gathers eta rows of ALL items ----
-    {
-      SegArgs a{sh.useg_dev, sh.uadj_dev, sh.usched_dev, table_ptr(mine, g, cur, g.eta[2]), wg_u, slots_u, d.pmax_u,
-                d.lmax_u, d.smax_u, Uo, sh.n_items, d.ldl, R, 0, 0, 0, dyn ? counters : nullptr};
-      if ((rc = launch_segment_pass_and_fixup(a, table_ptr(mine, g, cur, g.eta[1]),
-                                              table_ptr(mine, g, cur, g.eta[0]), sh.n_ratings_u, S, st))) return rc;
-    }
-    if ((rc = launch_n(wg_u, pn_u, th, sh.udeg_dev, th_n, Uo, d.ldk, d.rnb_u, 1, S, st))) return rc;
-    // theta' of the own users -> every rank's next tables; the DMA overlaps the by-item pass
-    if ((rc = publish_side(sh, g, g.theta, 2, th_n, Uo, sh.user_lo, nxt, st, ps))) return rc;
-    // ---- by-item pass over the own items: gathers theta rows of ALL users ----
-    {
-      SegArgs a{sh.iseg_dev, sh.iadj_dev, sh.isched_dev, table_ptr(mine, g, cur, g.theta[1]), wg_i, slots_i, d.pmax_i,
-                d.lmax_i, d.smax_i, Io, sh.n_users, d.ldk, R, 0, 0, 0, dyn ? counters + d.ctr / 2 : nullptr};
-      if ((rc = launch_segment_pass_and_fixup(a, table_ptr(mine, g, cur, g.theta[0]), nullptr,
-                                              sh.n_ratings_i, S, st))) return rc;
-    }
-    if ((rc = launch_n(wg_i, pn_i, et, sh.ideg_dev, et_n, Io, d.ldl, d.rnb_i, 1, S, st))) return rc;
-    if ((rc = publish_side(sh, g, g.eta, 3, et_n, Io, sh.item_lo, nxt, st, ps))) return rc;
-    // ---- n_pr: partial over the own segments of the emitting side, summed over the ranks ----
-    if ((rc = launch_pr(d.emit_items ? et : th, d.emit_items ? wg_i : wg_u, partial, pr, pr_n,
-                        d.emit_items ? Io : Uo, d.emit_items ? L : K, d.emit_items ? d.ldl : d.ldk,
-                        d.emit_items ? d.ldk : d.ldl, K, L, R, S, d.emit_items, sh.world == 1, st))) return rc;
-    if (prof) MMSBM_CUDA(cudaEventRecord(ev[1], st));
-    if (sh.world > 1) {
-      MMSBM_CUDA(cudaEventRecord(ps.pushed, ps.cs));
-      MMSBM_CUDA(cudaStreamWaitEvent(st, ps.pushed, 0));      // this rank's slices have landed everywhere
+    MMSBM_MARK(1);
+    // ---- pass 1 ----
+    if ((rc = users_first ? pass_users() : pass_items())) return rc;
+    MMSBM_MARK(2);
+    if ((rc = users_first ? finish_users() : finish_items())) return rc;
+    if (alternate) {
+      if ((rc = emit_pr())) return rc;
+      MMSBM_CUDA(cudaEventRecord(ex.partial, st));
+      MMSBM_CUDA(cudaStreamWaitEvent(ex.side, ex.partial, 0));
       MMSBM_NCCL(g_nccl.AllReduce(pr_n, pr_n, (size_t)S * K * L * R, ncclFloat64, ncclSum,
-                                  static_cast<ncclComm_t>(sh.nccl_comm), st));
+                                  static_cast<ncclComm_t>(sh.nccl_comm), ex.side));
+      MMSBM_CUDA(cudaEventRecord(ex.pr_done, ex.side));
+    }
+    if ((rc = after_publish(users_first ? 0 : 1))) return rc;
+    MMSBM_MARK(3);
+    // ---- pass 2 ----
+    if ((rc = users_first ? pass_items() : pass_users())) return rc;
+    MMSBM_MARK(4);
+    if ((rc = users_first ? finish_items() : finish_users())) return rc;
+    if (!alternate) {
+      if ((rc = emit_pr())) return rc;
+      if (peers) {                              // MMSBM_SHARD_ALTERNATE=0: the all-reduce is exposed
+        MMSBM_CUDA(cudaEventRecord(ex.partial, st));
+        MMSBM_CUDA(cudaStreamWaitEvent(ex.side, ex.partial, 0));
+        MMSBM_NCCL(g_nccl.AllReduce(pr_n, pr_n, (size_t)S * K * L * R, ncclFloat64, ncclSum,
+                                    static_cast<ncclComm_t>(sh.nccl_comm), ex.side));
+        MMSBM_CUDA(cudaEventRecord(ex.pr_done, ex.side));
+      }
+    }
+    if ((rc = after_publish(users_first ? 1 : 0))) return rc;
+    MMSBM_MARK(5);
+    if (peers) {
+      MMSBM_CUDA(cudaStreamWaitEvent(st, ex.pr_done, 0));
       if ((rc = launch_finalize_pr(pr_n, S * K * L, R, st))) return rc;
+      have_arrival[0] = have_arrival[1] = true;  // from now on every pass waits for the previous iteration's barrier
     }
+    MMSBM_MARK(6);
     if (prof) {
-      MMSBM_CUDA(cudaEventRecord(ev[2], st));
-      MMSBM_CUDA(cudaEventSynchronize(ev[2]));
-      float a = 0.f, b = 0.f;
-      cudaEventElapsedTime(&a, ev[0], ev[2]);
-      cudaEventElapsedTime(&b, ev[1], ev[2]);
-      prof_iter += a; prof_exch += b;
+      MMSBM_CUDA(cudaEventSynchronize(ev[6]));
+      float t = 0.f;
+      cudaEventElapsedTime(&t, ev[0], ev[6]); acc[0] += t;
+      cudaEventElapsedTime(&t, ev[5], ev[6]); acc[1] += t;
+      for (int k = 0; k < 5; ++k) { cudaEventElapsedTime(&t, ev[k], ev[k + 1]); acc[2 + k] += t; }
     }
   }
-  if (prof) {
-    prof[0] = iterations > 0 ? (float)(prof_iter / iterations) : 0.f;
-    prof[1] = iterations > 0 ? (float)(prof_exch / iterations) : 0.f;
+#undef MMSBM_MARK
+  if (peers && iterations > 0) {                // drain: every table complete everywhere before the call returns its stream
+    MMSBM_CUDA(cudaStreamWaitEvent(st, ex.arrived[0][(iterations - 1) & 1], 0));
+    MMSBM_CUDA(cudaStreamWaitEvent(st, ex.arrived[1][(iterations - 1) & 1], 0));
   }
-  // the copy stream is destroyed on return: its work is ordered before the last all-reduce on `st`
+  if (prof) for (int k = 0; k < 8; ++k) prof[k] = iterations > 0 ? (float)(acc[k] / iterations) : 0.f;
   return 0;
 }

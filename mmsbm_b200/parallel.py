@@ -142,6 +142,7 @@ def _nccl_library_path():
 
 
 _COMM_CACHE = {}          # (device, rank, world) -> ncclComm_t of this process (created once, kept)
+SEGMENT_COST = 48         # ratings an id is worth in the partition balance (see ShardedEngine)
 
 
 class ShardedEngine:
@@ -177,8 +178,13 @@ class ShardedEngine:
         self.N = base.N
         R = self.R
         with torch.cuda.device(self.device):
-            self.ub = balanced_partition(base.udeg[:self.U].cpu().numpy(), self.world)
-            self.ib = balanced_partition(base.ideg[:self.I].cpu().numpy(), self.world)
+            # balance = ratings + SEGMENT_COST per id: what an id costs besides its ratings (its W / G
+            # rows, the two contractions, the per-segment part of the pass) is worth about that many
+            # ratings (ML-20M shape: 4.5 ns per user-run against 0.125 ns per rating-update, plus the
+            # in-pass overhead); without it the rank that owns the long tail of a heavy-tailed id
+            # distribution does most of the per-id work (Zipf ids, 8 GPUs: 3.5 instead of 1.1 ms)
+            self.ub = balanced_partition(base.udeg[:self.U].cpu().numpy().astype(np.int64) + SEGMENT_COST, self.world)
+            self.ib = balanced_partition(base.ideg[:self.I].cpu().numpy().astype(np.int64) + SEGMENT_COST, self.world)
             self.ulo, self.uhi = int(self.ub[self.rank]), int(self.ub[self.rank + 1])
             self.ilo, self.ihi = int(self.ib[self.rank]), int(self.ib[self.rank + 1])
             self.Uo, self.Io = self.uhi - self.ulo, self.ihi - self.ilo
@@ -332,12 +338,14 @@ class ShardedEngine:
 
     def run(self, iterations, prof=False):
         """``iterations`` EM steps of all S runs (the loop lives in the library).  With ``prof``
-        returns (mean ms per iteration, mean ms of it waiting for the exchange + all-reduce)."""
+        returns the mean device ms per iteration of [whole iteration, wait for n_pr at its end,
+        P tables + W, pass 1, n + publish + pr partial, pass 2, n + publish, 0] (measuring
+        synchronises every iteration)."""
         iterations = int(iterations)
         if iterations <= 0:
             return None
         a, b = (self.theta, self.eta, self.pr), self._alt
-        out = (C.c_float * 2)() if prof else None
+        out = (C.c_float * 8)() if prof else None
         self._lib.check(self.lib.mmsbm_em_run_sharded(
             C.byref(self._shard_c), iterations, a[0].data_ptr(), a[1].data_ptr(), a[2].data_ptr(),
             b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(), self._half, self._ws.data_ptr(),
@@ -345,7 +353,7 @@ class ShardedEngine:
         if iterations % 2:
             (self.theta, self.eta, self.pr), self._alt = self._alt, (self.theta, self.eta, self.pr)
             self._half ^= 1
-        return (float(out[0]), float(out[1])) if prof else None
+        return [float(x) for x in out] if prof else None
 
     # ---------------------------------------------------------------- results
     def _full(self, own, lo, hi, n_all):

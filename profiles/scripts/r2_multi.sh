@@ -28,9 +28,9 @@ except Exception as e:
     print(sys.argv[1], "unreadable", e); raise SystemExit
 print(sys.argv[1], "value %.3e" % d["value"], "ms/step %.2f" % d["ms_per_step"], d["config"].get("mode"), d["config"].get("parallelism", "")[:60])
 for m, r in (d.get("modes") or {}).items():
-    print("   ", m, "%.3e" % r["value"], "ms/it %.4f" % r["ms_per_iteration"], {k: r[k] for k in ("exchange_wait_ms_per_iteration", "runs_per_gpu", "setup_s") if k in r})
+    print("   ", m, "%.3e" % r["value"], "ms/it %.4f" % r["ms_per_iteration"], {k: r[k] for k in ("pr_wait_ms_per_iteration", "runs_per_gpu", "setup_s", "stage_ms_when_profiled") if k in r})
 nf = d.get("netflix_ratings_sharded")
-if nf: print("    netflix %.3e" % nf["value"], "ms/it %.4f" % nf["ms_per_iteration"], "wait", nf["exchange_wait_ms_per_iteration"], "lik diff", nf.get("likelihood_rel_diff_vs_one_gpu"))
+if nf: print("    netflix %.3e" % nf["value"], "ms/it %.4f" % nf["ms_per_iteration"], "wait", nf["pr_wait_ms_per_iteration"], nf["stage_ms_when_profiled"], "lik diff", nf.get("likelihood_rel_diff_vs_one_gpu"))
 if d.get("e2e"): print("    e2e %.3e" % d["e2e"]["value"], "ms/step %.1f" % d["e2e"]["ms_per_step"])
 if "cv_accuracies" in d: print("    cv", d["cv_accuracies"], d["wall_s_per_cv"], d["config"]["parallelism"])
 PY
