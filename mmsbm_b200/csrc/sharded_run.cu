@@ -368,9 +368,9 @@ extern "C" int mmsbm_shard_publish(const mmsbm_shard_t* sh, const double* theta_
 // Passes ALTERNATE their order from one iteration to the next (by-user, by-item | by-item, by-user | ...):
 // the table a first pass gathers was pushed during the previous iteration's second pass, and the one a
 // second pass gathers was pushed at the very end of the previous iteration and has the whole first pass to
-// arrive, so no push and no barrier is waited for.  n_pr is emitted by the side of pass 1 so that its
-// all-reduce hides behind pass 2.  With world == 1 nothing of this applies: fixed order, n_pr from the side
-// with fewer segments and normalised in place -- bit for bit what mmsbm_em_run computes.
+// arrive, so no push and no barrier is waited for.  n_pr always comes from the side with fewer segments;
+// in the iterations where that side is pass 1 its all-reduce hides behind pass 2.  With world == 1 nothing
+// of this applies: fixed order, n_pr normalised in place -- bit for bit what mmsbm_em_run computes.
 //
 // prof (optional, 8 floats): mean device ms per iteration of {whole iteration, wait for n_pr at its end,
 // P tables + W, pass 1, n + publish + pr partial, (wait +) pass 2, n + publish, unused}; measuring
@@ -442,8 +442,11 @@ extern "C" int mmsbm_em_run_sharded(const mmsbm_shard_t* shp, int32_t iterations
     const double* pr = fwd ? pr_a : pr_b;
     double* th_n = fwd ? theta_b : theta_a; double* et_n = fwd ? eta_b : eta_a; double* pr_n = fwd ? pr_b : pr_a;
     const bool users_first = !alternate || (it & 1) == 0;
-    // n_pr comes from the g rows of ONE side: of pass 1 with peers, of the side with fewer segments alone
-    const bool emit_items = alternate ? !users_first : d.emit_items;
+    // n_pr comes from the g rows of the side with fewer segments (accumulating over 480k users instead of
+    // 17.7k items costs more than an exposed all-reduce); when that side is pass 1 its all-reduce hides
+    // behind pass 2
+    const bool emit_items = d.emit_items;
+    const bool emit_after_pass1 = peers && (emit_items != users_first);
 
     auto pass_users = [&]() -> int {            // gathers eta rows of ALL items, new theta rows of the own users
       if (have_arrival[1]) MMSBM_CUDA(cudaStreamWaitEvent(st, ex.arrived[1][(it + 1) & 1], 0));
@@ -489,30 +492,24 @@ extern "C" int mmsbm_em_run_sharded(const mmsbm_shard_t* shp, int32_t iterations
     if ((rc = users_first ? pass_users() : pass_items())) return rc;
     MMSBM_MARK(2);
     if ((rc = users_first ? finish_users() : finish_items())) return rc;
-    if (alternate) {
-      if ((rc = emit_pr())) return rc;
+    auto reduce_pr = [&]() -> int {             // partial n_pr on st, its sum over the ranks on the side stream
+      int r = emit_pr();
+      if (r || !peers) return r;
       MMSBM_CUDA(cudaEventRecord(ex.partial, st));
       MMSBM_CUDA(cudaStreamWaitEvent(ex.side, ex.partial, 0));
       MMSBM_NCCL(g_nccl.AllReduce(pr_n, pr_n, (size_t)S * K * L * R, ncclFloat64, ncclSum,
                                   static_cast<ncclComm_t>(sh.nccl_comm), ex.side));
       MMSBM_CUDA(cudaEventRecord(ex.pr_done, ex.side));
-    }
+      return 0;
+    };
+    if (emit_after_pass1 && (rc = reduce_pr())) return rc;
     if ((rc = after_publish(users_first ? 0 : 1))) return rc;
     MMSBM_MARK(3);
     // ---- pass 2 ----
     if ((rc = users_first ? pass_items() : pass_users())) return rc;
     MMSBM_MARK(4);
     if ((rc = users_first ? finish_items() : finish_users())) return rc;
-    if (!alternate) {
-      if ((rc = emit_pr())) return rc;
-      if (peers) {                              // MMSBM_SHARD_ALTERNATE=0: the all-reduce is exposed
-        MMSBM_CUDA(cudaEventRecord(ex.partial, st));
-        MMSBM_CUDA(cudaStreamWaitEvent(ex.side, ex.partial, 0));
-        MMSBM_NCCL(g_nccl.AllReduce(pr_n, pr_n, (size_t)S * K * L * R, ncclFloat64, ncclSum,
-                                    static_cast<ncclComm_t>(sh.nccl_comm), ex.side));
-        MMSBM_CUDA(cudaEventRecord(ex.pr_done, ex.side));
-      }
-    }
+    if (!emit_after_pass1 && (rc = reduce_pr())) return rc;   // (exposed: nothing left to hide it behind)
     if ((rc = after_publish(users_first ? 1 : 0))) return rc;
     MMSBM_MARK(5);
     if (peers) {
