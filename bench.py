@@ -597,7 +597,7 @@ def sharded_record(cx, data, shape, T, steps, warmup, check_single_gpu):
            "ms_per_iteration": ms / steps / T, "ms_per_step": ms / steps,
            "pr_wait_ms_per_iteration": cx.max_over_ranks(prof[1]),
            "stage_ms_when_profiled": dict(zip(("iteration", "wait_n_pr", "p_tables_w", "pass_1", "n_publish_pr_1",
-                                               "pass_2", "n_publish_2"), [cx.max_over_ranks(x) for x in prof[:7]])),
+                                               "pass_2", "n_publish_2", "host_issue"), [cx.max_over_ranks(x) for x in prof[:8]])),
            "exchange": "theta / eta rows: copy-engine DMA into every peer's exchange buffer (CUDA IPC over "
                        "NVLink, one copy stream per peer), overlapped with the other pass (the passes alternate "
                        f"their order); one ncclAllReduce of n_pr ({S * K * L * R * 8} bytes) and two one-element "

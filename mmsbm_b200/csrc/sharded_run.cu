@@ -25,6 +25,8 @@
 // Sums have a fixed order for a fixed world size; vs one GPU only the n_pr order differs.
 #include <dlfcn.h>
 #include <nccl.h>
+
+#include <chrono>
 #include <stdlib.h>
 #include <string.h>
 
@@ -373,7 +375,8 @@ extern "C" int mmsbm_shard_publish(const mmsbm_shard_t* sh, const double* theta_
 // of this applies: fixed order, n_pr normalised in place -- bit for bit what mmsbm_em_run computes.
 //
 // prof (optional, 8 floats): mean device ms per iteration of {whole iteration, wait for n_pr at its end,
-// P tables + W, pass 1, n + publish + pr partial, (wait +) pass 2, n + publish, unused}; measuring
+// P tables + W, pass 1, n + publish + pr partial, (wait +) pass 2, n + publish} and the HOST ms it took to issue
+// an iteration; measuring
 // synchronises every iteration (which serialises the overlap: stage times, not a throughput figure).
 extern "C" int mmsbm_em_run_sharded(const mmsbm_shard_t* shp, int32_t iterations, double* theta_a, double* eta_a,
                                     double* pr_a, double* theta_b, double* eta_b, double* pr_b, int32_t half,
@@ -482,6 +485,7 @@ extern "C" int mmsbm_em_run_sharded(const mmsbm_shard_t* shp, int32_t iterations
       return barrier_on_side(sh, g, ex, ex.arrived[which][it & 1]);
     };
 
+    const auto host_t0 = std::chrono::steady_clock::now();
     MMSBM_MARK(0);
     if (dyn) MMSBM_CUDA(cudaMemsetAsync(counters, 0, d.ctr * 4, st));
     if ((rc = launch_prep_p(pr, K, L, R, d.ldk, d.ldl, S, pw_u, pn_u, pw_i, pn_i, st))) return rc;
@@ -519,6 +523,7 @@ extern "C" int mmsbm_em_run_sharded(const mmsbm_shard_t* shp, int32_t iterations
     }
     MMSBM_MARK(6);
     if (prof) {
+      acc[7] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
       MMSBM_CUDA(cudaEventSynchronize(ev[6]));
       float t = 0.f;
       cudaEventElapsedTime(&t, ev[0], ev[6]); acc[0] += t;

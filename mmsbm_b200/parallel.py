@@ -156,12 +156,19 @@ class ShardedEngine:
     range (positions in ``seg`` are absolute, so ``adj`` is shared) plus a schedule built for the
     range alone (``mmsbm_sched_build``).  No host-side row shuffling."""
 
-    def __init__(self, data, n_users, n_items, n_levels, K, L, device=None):
+    def __init__(self, data, n_users, n_items, n_levels, K, L, device=None, pretend=None):
+        """``pretend=(rank, world)`` (measurement only, one process): take the ranges rank ``rank`` of
+        ``world`` would own, with no peers -- the gather tables are filled once from all rows and
+        then only the own slices are refreshed, so the NUMBERS are meaningless after the first
+        iteration but the kernels do exactly one rank's work (profiles/scripts/rank_compute.py)."""
         from . import _lib
         from .engine import Engine
         self._lib = _lib
         self.lib = _lib.load(require_device=True)
         self.rank, self.world = dist_info()
+        self._pretend = pretend
+        if pretend is not None:
+            self.rank, self.world = int(pretend[0]), int(pretend[1])
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
             else torch.device(device)
         self.U, self.I, self.R, self.K, self.L = int(n_users), int(n_items), int(n_levels), int(K), int(L)
@@ -195,8 +202,11 @@ class ShardedEngine:
             self.iseg, self.iadj, self.ideg = base.iseg[self.ilo * R:], base.iadj, base.ideg[self.ilo:]
             self.usched = self._build_sched(self.udeg, self.Uo, self.Nu)
             self.isched = self._build_sched(self.ideg, self.Io, self.Ni)
-            if self.world > 1:
+            if self.world > 1 and pretend is None:
                 self._open_nccl()
+        if pretend is not None:                 # the library sees a single rank that owns a sub-range
+            self._true_world, self.world = self.world, 1
+            self.rank = 0
 
     # ------------------------------------------------------------------ set-up
     def _stream(self):
@@ -327,6 +337,14 @@ class ShardedEngine:
                                 "shard_workspace_bytes")
                 self._ws = torch.empty(max(need.value, 16), dtype=torch.uint8, device=dev)
                 self._ws_bytes = need.value
+            if self._pretend is not None:       # fill the tables from ALL rows once (a shard that owns everything)
+                full = self._shard()
+                full.n_users_own, full.user_lo, full.n_items_own, full.item_lo = self.U, 0, self.I, 0
+                th_all = torch.from_numpy(self._pad(theta, self.ldk)).to(dev)
+                et_all = torch.from_numpy(self._pad(eta, self.ldl)).to(dev)
+                self._lib.check(self.lib.mmsbm_shard_publish(C.byref(full), th_all.data_ptr(), et_all.data_ptr(),
+                                                             0, self._stream()), "shard_publish (all rows)")
+                torch.cuda.synchronize(dev)
             self.theta = torch.from_numpy(self._pad(theta[:, self.ulo:self.uhi], self.ldk)).to(dev)
             self.eta = torch.from_numpy(self._pad(eta[:, self.ilo:self.ihi], self.ldl)).to(dev)
             self.pr = torch.from_numpy(np.ascontiguousarray(pr, dtype=np.float64)).to(dev)
