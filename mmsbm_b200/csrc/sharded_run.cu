@@ -102,6 +102,8 @@ static const double* table_ptr(const void* base, const GridLayout& g, int half, 
 struct Exchange {
   int peers = 0;
   cudaStream_t side = nullptr;
+  cudaStream_t aux = nullptr;                   // high priority: epilogue of pass 1 beside pass 2
+  cudaEvent_t p_ready = nullptr, w2_ready = nullptr, pass1_done = nullptr, aux_done = nullptr;
   cudaStream_t cp[16] = {nullptr};
   cudaEvent_t ready = nullptr;                  // main -> copy streams: the slice is in the own tables
   cudaEvent_t done[16] = {nullptr};             // copy stream p -> side: its copies have been issued and finished
@@ -115,22 +117,30 @@ struct Exchange {
     if (peers <= 0) return 0;
     MMSBM_REQUIRE(peers <= 16, MMSBM_ERANGE, "sharded runs support up to 17 ranks");
     MMSBM_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    {
+      int lo = 0, hi = 0;                       // (numerically lowest = highest priority)
+      MMSBM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      MMSBM_CUDA(cudaStreamCreateWithPriority(&aux, cudaStreamNonBlocking, hi));
+    }
     for (int p = 0; p < peers; ++p) {
       MMSBM_CUDA(cudaStreamCreateWithFlags(&cp[p], cudaStreamNonBlocking));
       MMSBM_CUDA(cudaEventCreateWithFlags(&done[p], cudaEventDisableTiming));
     }
-    cudaEvent_t* evs[] = {&ready, &partial, &pr_done, &arrived[0][0], &arrived[0][1], &arrived[1][0], &arrived[1][1]};
+    cudaEvent_t* evs[] = {&ready, &partial, &pr_done, &arrived[0][0], &arrived[0][1], &arrived[1][0], &arrived[1][1],
+                          &p_ready, &w2_ready, &pass1_done, &aux_done};
     for (cudaEvent_t* e : evs) MMSBM_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     return 0;
   }
   ~Exchange() {                                 // queued work finishes first: handles are released lazily
-    cudaEvent_t evs[] = {ready, partial, pr_done, arrived[0][0], arrived[0][1], arrived[1][0], arrived[1][1]};
+    cudaEvent_t evs[] = {ready, partial, pr_done, arrived[0][0], arrived[0][1], arrived[1][0], arrived[1][1],
+                         p_ready, w2_ready, pass1_done, aux_done};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     for (int p = 0; p < peers; ++p) {
       if (done[p]) cudaEventDestroy(done[p]);
       if (cp[p]) cudaStreamDestroy(cp[p]);
     }
     if (side) cudaStreamDestroy(side);
+    if (aux) cudaStreamDestroy(aux);
   }
 };
 
@@ -428,6 +438,7 @@ extern "C" int mmsbm_em_run_sharded(const mmsbm_shard_t* shp, int32_t iterations
   const int64_t n_big = sh.n_ratings_u > sh.n_ratings_i ? sh.n_ratings_u : sh.n_ratings_i;
   const bool dyn = env_int("MMSBM_DYN", n_big >= ((int64_t)1 << 22) ? 1 : 0) != 0;
   const bool alternate = peers && env_int("MMSBM_SHARD_ALTERNATE", 1) != 0;
+  const bool overlap = peers && env_int("MMSBM_SHARD_OVERLAP", 1) != 0;   // aux stream beside the main one
   // persistent CTAs of the passes leave a few slots free so that the NCCL kernels of the side stream
   // can start while a pass runs
   if (peers) set_reserved_ctas(env_int("MMSBM_SHARD_RESERVE", 4));
@@ -451,6 +462,8 @@ extern "C" int mmsbm_em_run_sharded(const mmsbm_shard_t* shp, int32_t iterations
     const bool emit_items = d.emit_items;
     const bool emit_after_pass1 = peers && (emit_items != users_first);
 
+    // what follows a pass (n contraction, interleave into the next tables, push, n_pr partial) runs on `fs`:
+    // the main stream, or -- after pass 1, with peers -- the AUX stream, so that it overlaps pass 2
     auto pass_users = [&]() -> int {            // gathers eta rows of ALL items, new theta rows of the own users
       if (have_arrival[1]) MMSBM_CUDA(cudaStreamWaitEvent(st, ex.arrived[1][(it + 1) & 1], 0));
       SegArgs a{sh.useg_dev, sh.uadj_dev, sh.usched_dev, table_ptr(mine, g, cur, g.eta[2]), wg_u, slots_u, d.pmax_u,
@@ -458,11 +471,10 @@ extern "C" int mmsbm_em_run_sharded(const mmsbm_shard_t* shp, int32_t iterations
       return launch_segment_pass_and_fixup(a, table_ptr(mine, g, cur, g.eta[1]), table_ptr(mine, g, cur, g.eta[0]),
                                            sh.n_ratings_u, S, st);
     };
-    auto finish_users = [&]() -> int {
-      int r = launch_n(wg_u, pn_u, th, sh.udeg_dev, th_n, Uo, d.ldk, d.rnb_u, 1, S, st);
+    auto finish_users = [&](cudaStream_t fs) -> int {
+      int r = launch_n(wg_u, pn_u, th, sh.udeg_dev, th_n, Uo, d.ldk, d.rnb_u, 1, S, fs);
       if (r) return r;
-      if ((r = publish_side(sh, g, g.theta, 2, th_n, Uo, sh.user_lo, nxt, st, ex))) return r;
-      return 0;
+      return publish_side(sh, g, g.theta, 2, th_n, Uo, sh.user_lo, nxt, fs, ex);
     };
     auto pass_items = [&]() -> int {            // gathers theta rows of ALL users, new eta rows of the own items
       if (have_arrival[0]) MMSBM_CUDA(cudaStreamWaitEvent(st, ex.arrived[0][(it + 1) & 1], 0));
@@ -470,52 +482,67 @@ extern "C" int mmsbm_em_run_sharded(const mmsbm_shard_t* shp, int32_t iterations
                 d.lmax_i, d.smax_i, Io, sh.n_users, d.ldk, R, 0, 0, 0, dyn ? counters + d.ctr / 2 : nullptr};
       return launch_segment_pass_and_fixup(a, table_ptr(mine, g, cur, g.theta[0]), nullptr, sh.n_ratings_i, S, st);
     };
-    auto finish_items = [&]() -> int {
-      int r = launch_n(wg_i, pn_i, et, sh.ideg_dev, et_n, Io, d.ldl, d.rnb_i, 1, S, st);
+    auto finish_items = [&](cudaStream_t fs) -> int {
+      int r = launch_n(wg_i, pn_i, et, sh.ideg_dev, et_n, Io, d.ldl, d.rnb_i, 1, S, fs);
       if (r) return r;
-      return publish_side(sh, g, g.eta, 3, et_n, Io, sh.item_lo, nxt, st, ex);
+      return publish_side(sh, g, g.eta, 3, et_n, Io, sh.item_lo, nxt, fs, ex);
     };
-    auto emit_pr = [&]() -> int {               // partial n_pr over the own segments of the emitting side
-      return launch_pr(emit_items ? et : th, emit_items ? wg_i : wg_u, partial, pr, pr_n, emit_items ? Io : Uo,
-                       emit_items ? L : K, emit_items ? d.ldl : d.ldk, emit_items ? d.ldk : d.ldl, K, L, R, S,
-                       emit_items, !peers, st);
-    };
-    auto after_publish = [&](int which) -> int {   // side stream: [n_pr all-reduce,] arrival barrier of table `which`
-      if (!peers) return 0;
-      return barrier_on_side(sh, g, ex, ex.arrived[which][it & 1]);
-    };
-
-    const auto host_t0 = std::chrono::steady_clock::now();
-    MMSBM_MARK(0);
-    if (dyn) MMSBM_CUDA(cudaMemsetAsync(counters, 0, d.ctr * 4, st));
-    if ((rc = launch_prep_p(pr, K, L, R, d.ldk, d.ldl, S, pw_u, pn_u, pw_i, pn_i, st))) return rc;
-    if ((rc = launch_w(th, pw_u, wg_u, Uo, d.ldk, d.rnb_u, S, st))) return rc;
-    if ((rc = launch_w(et, pw_i, wg_i, Io, d.ldl, d.rnb_i, S, st))) return rc;
-    MMSBM_MARK(1);
-    // ---- pass 1 ----
-    if ((rc = users_first ? pass_users() : pass_items())) return rc;
-    MMSBM_MARK(2);
-    if ((rc = users_first ? finish_users() : finish_items())) return rc;
-    auto reduce_pr = [&]() -> int {             // partial n_pr on st, its sum over the ranks on the side stream
-      int r = emit_pr();
+    auto reduce_pr = [&](cudaStream_t fs) -> int {   // partial n_pr on fs, its sum over the ranks on the side stream
+      int r = launch_pr(emit_items ? et : th, emit_items ? wg_i : wg_u, partial, pr, pr_n, emit_items ? Io : Uo,
+                        emit_items ? L : K, emit_items ? d.ldl : d.ldk, emit_items ? d.ldk : d.ldl, K, L, R, S,
+                        emit_items, !peers, fs);
       if (r || !peers) return r;
-      MMSBM_CUDA(cudaEventRecord(ex.partial, st));
+      MMSBM_CUDA(cudaEventRecord(ex.partial, fs));
       MMSBM_CUDA(cudaStreamWaitEvent(ex.side, ex.partial, 0));
       MMSBM_NCCL(g_nccl.AllReduce(pr_n, pr_n, (size_t)S * K * L * R, ncclFloat64, ncclSum,
                                   static_cast<ncclComm_t>(sh.nccl_comm), ex.side));
       MMSBM_CUDA(cudaEventRecord(ex.pr_done, ex.side));
       return 0;
     };
-    if (emit_after_pass1 && (rc = reduce_pr())) return rc;
+    auto after_publish = [&](int which) -> int {   // side stream: arrival barrier of table `which`
+      if (!peers) return 0;
+      return barrier_on_side(sh, g, ex, ex.arrived[which][it & 1]);
+    };
+    cudaStream_t aux = overlap ? ex.aux : st;
+
+    const auto host_t0 = std::chrono::steady_clock::now();
+    MMSBM_MARK(0);
+    if (dyn) MMSBM_CUDA(cudaMemsetAsync(counters, 0, d.ctr * 4, st));
+    if ((rc = launch_prep_p(pr, K, L, R, d.ldk, d.ldl, S, pw_u, pn_u, pw_i, pn_i, st))) return rc;
+    if (overlap) {                              // W of pass 2's side on the aux stream, beside pass 1
+      MMSBM_CUDA(cudaEventRecord(ex.p_ready, st));
+      MMSBM_CUDA(cudaStreamWaitEvent(aux, ex.p_ready, 0));
+    }
+    if (users_first) {
+      if ((rc = launch_w(th, pw_u, wg_u, Uo, d.ldk, d.rnb_u, S, st))) return rc;
+      if ((rc = launch_w(et, pw_i, wg_i, Io, d.ldl, d.rnb_i, S, aux))) return rc;
+    } else {
+      if ((rc = launch_w(et, pw_i, wg_i, Io, d.ldl, d.rnb_i, S, st))) return rc;
+      if ((rc = launch_w(th, pw_u, wg_u, Uo, d.ldk, d.rnb_u, S, aux))) return rc;
+    }
+    if (overlap) MMSBM_CUDA(cudaEventRecord(ex.w2_ready, aux));
+    MMSBM_MARK(1);
+    // ---- pass 1; its epilogue goes to the aux stream ----
+    if ((rc = users_first ? pass_users() : pass_items())) return rc;
+    MMSBM_MARK(2);
+    if (overlap) {
+      MMSBM_CUDA(cudaEventRecord(ex.pass1_done, st));
+      MMSBM_CUDA(cudaStreamWaitEvent(aux, ex.pass1_done, 0));
+    }
+    if ((rc = users_first ? finish_users(aux) : finish_items(aux))) return rc;
+    if (emit_after_pass1 && (rc = reduce_pr(aux))) return rc;
     if ((rc = after_publish(users_first ? 0 : 1))) return rc;
+    if (overlap) MMSBM_CUDA(cudaEventRecord(ex.aux_done, aux));
     MMSBM_MARK(3);
     // ---- pass 2 ----
+    if (overlap) MMSBM_CUDA(cudaStreamWaitEvent(st, ex.w2_ready, 0));
     if ((rc = users_first ? pass_items() : pass_users())) return rc;
     MMSBM_MARK(4);
-    if ((rc = users_first ? finish_items() : finish_users())) return rc;
-    if (!emit_after_pass1 && (rc = reduce_pr())) return rc;   // (exposed: nothing left to hide it behind)
+    if ((rc = users_first ? finish_items(st) : finish_users(st))) return rc;
+    if (!emit_after_pass1 && (rc = reduce_pr(st))) return rc;   // (exposed: nothing left to hide it behind)
     if ((rc = after_publish(users_first ? 1 : 0))) return rc;
     MMSBM_MARK(5);
+    if (overlap) MMSBM_CUDA(cudaStreamWaitEvent(st, ex.aux_done, 0));
     if (peers) {
       MMSBM_CUDA(cudaStreamWaitEvent(st, ex.pr_done, 0));
       if ((rc = launch_finalize_pr(pr_n, S * K * L, R, st))) return rc;
