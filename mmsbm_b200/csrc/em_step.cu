@@ -260,113 +260,6 @@ __global__ void __launch_bounds__(kRowThreads) row_w_kernel(const double* __rest
   }
 }
 
-// SPLIT lanes per row: lane `part` computes the 32-byte output chunks part, part + SPLIT, ... of its row.
-// Used when there are few rows (a rank of a sharded run, small problems): with one lane per row a lane
-// does all LD * RNB multiply-adds of its row alone and the kernel is one short wave bound by that
-// serial chain; SPLIT lanes shorten the chain SPLIT times and the SPLIT chunks a row's lanes store
-// in one step are contiguous.
-template <int LD, int SPLIT>
-__global__ void __launch_bounds__(kRowThreads) row_w_split_kernel(const double* __restrict__ own,
-                                                                  const double* __restrict__ pw,
-                                                                  double* __restrict__ W, int M, int RNB) {
-  extern __shared__ __align__(32) unsigned char smem_raw[];
-  double* Ps = reinterpret_cast<double*>(smem_raw);          // [LD][RNB]
-  const int run = blockIdx.y;
-  {
-    const double2* src = reinterpret_cast<const double2*>(pw + (size_t)run * LD * RNB);
-    double2* dst = reinterpret_cast<double2*>(Ps);
-    for (int t = threadIdx.x; t < (LD * RNB) >> 1; t += kRowThreads) dst[t] = __ldg(src + t);
-  }
-  __syncthreads();
-  const double* own_run = own + (size_t)run * M * LD;
-  double* w_run = W + (size_t)run * M * RNB;
-  constexpr int kRowsPerCta = kRowThreads / SPLIT;
-  const int part = threadIdx.x % SPLIT;
-  for (int m = blockIdx.x * kRowsPerCta + threadIdx.x / SPLIT; m < M; m += gridDim.x * kRowsPerCta) {
-    double o[LD];
-#pragma unroll
-    for (int c = 0; c < LD / 4; ++c) {
-      const double4_t v = ldg256(own_run + (size_t)m * LD + 4 * c);
-      o[4 * c] = v.x; o[4 * c + 1] = v.y; o[4 * c + 2] = v.z; o[4 * c + 3] = v.w;
-    }
-    for (int ob = 4 * part; ob < RNB; ob += 4 * SPLIT) {
-      double4_t acc{0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-      for (int a = 0; a < LD; ++a) {
-        const double4_t p = lds32(Ps + a * RNB + ob);
-        acc.x = fma(o[a], p.x, acc.x); acc.y = fma(o[a], p.y, acc.y);
-        acc.z = fma(o[a], p.z, acc.z); acc.w = fma(o[a], p.w, acc.w);
-      }
-      stg256(w_run + (size_t)m * RNB + ob, acc);
-    }
-  }
-}
-
-// The n contraction with SPLIT lanes per row: lane `part` takes the G chunks part, part + SPLIT, ...
-// (the lanes of a row read consecutive 32-byte chunks), the partial sums are added over the SPLIT
-// lanes by xor shuffles in a fixed order, lane 0 of the row applies the epilogue.  Same use as
-// row_w_split_kernel.  The sum over o is associated differently from the one-lane kernel (last-bit
-// differences); which kernel runs depends only on the shape, so results stay reproducible.
-template <int LD, int SPLIT>
-__global__ void __launch_bounds__(kRowThreads) row_n_split_kernel(const double* __restrict__ G,
-                                                                  const double* __restrict__ pn,
-                                                                  const double* __restrict__ own,
-                                                                  const int32_t* __restrict__ deg,
-                                                                  double* __restrict__ out, int M, int RNB,
-                                                                  int normalize) {
-  static_assert(SPLIT == 2 || SPLIT == 4 || SPLIT == 8, "power-of-two lane groups");
-  extern __shared__ __align__(32) unsigned char smem_raw[];
-  double* Ps = reinterpret_cast<double*>(smem_raw);          // [RNB][LD]
-  const int run = blockIdx.y;
-  {
-    const double2* src = reinterpret_cast<const double2*>(pn + (size_t)run * LD * RNB);
-    double2* dst = reinterpret_cast<double2*>(Ps);
-    for (int t = threadIdx.x; t < (LD * RNB) >> 1; t += kRowThreads) dst[t] = __ldg(src + t);
-  }
-  __syncthreads();
-  const double* g_run = G + (size_t)run * M * RNB;
-  const double* own_run = own + (size_t)run * M * LD;
-  double* out_run = out + (size_t)run * M * LD;
-  constexpr int kRowsPerCta = kRowThreads / SPLIT;
-  const int part = threadIdx.x % SPLIT;
-  const int rows_total = (M + kRowsPerCta - 1) / kRowsPerCta * kRowsPerCta;   // whole warps stay in the loop (shuffles)
-  for (int m = blockIdx.x * kRowsPerCta + threadIdx.x / SPLIT; m < rows_total; m += gridDim.x * kRowsPerCta) {
-    const int mc = m < M ? m : M - 1;                        // rows past the end recompute the last row
-    const double* grow = g_run + (size_t)mc * RNB;
-    double acc[LD];
-#pragma unroll
-    for (int a = 0; a < LD; ++a) acc[a] = 0.0;
-    for (int ob = 4 * part; ob < RNB; ob += 4 * SPLIT) {
-      const double4_t gq = ldg256(grow + ob);
-      const double gv[4] = {gq.x, gq.y, gq.z, gq.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-#pragma unroll
-        for (int c = 0; c < LD / 4; ++c) {
-          const double4_t pv = lds32(Ps + (ob + i) * LD + 4 * c);
-          acc[4 * c] = fma(gv[i], pv.x, acc[4 * c]);         acc[4 * c + 1] = fma(gv[i], pv.y, acc[4 * c + 1]);
-          acc[4 * c + 2] = fma(gv[i], pv.z, acc[4 * c + 2]); acc[4 * c + 3] = fma(gv[i], pv.w, acc[4 * c + 3]);
-        }
-      }
-    }
-#pragma unroll
-    for (int off = 1; off < SPLIT; off <<= 1)
-#pragma unroll
-      for (int a = 0; a < LD; ++a) acc[a] += __shfl_xor_sync(kFull, acc[a], off);
-    if (part == 0 && m < M) {
-      double dd = 1.0;
-      if (normalize) dd = (double)max(__ldg(deg + m), 1);
-#pragma unroll
-      for (int c = 0; c < LD / 4; ++c) {
-        const double4_t ov = ldg256(own_run + (size_t)m * LD + 4 * c);
-        double4_t v{acc[4 * c] * ov.x, acc[4 * c + 1] * ov.y, acc[4 * c + 2] * ov.z, acc[4 * c + 3] * ov.w};
-        if (normalize) { v.x = v.x / dd; v.y = v.y / dd; v.z = v.z / dd; v.w = v.w / dd; }
-        stg256(out_run + (size_t)m * LD + 4 * c, v);
-      }
-    }
-  }
-}
-
 // PF chunks (32 bytes each) of the G row are loaded back to back before any of them is used: a lane
 // then has PF loads in flight instead of one, which is what the HBM stream of this kernel needs
 // (lane-per-row rows are 800 bytes apart, so memory-level parallelism has to come from depth).
@@ -800,22 +693,6 @@ int launch_w(const double* own, const double* pw, double* W, int M, int LD, int 
              cudaStream_t st) {
   const size_t smem = (size_t)LD * RNB * 8;
   const int rows_env = env_int("MMSBM_ROWS", 2);
-  // few rows (less than ~3 per resident lane): four lanes per row (row_w_split_kernel)
-  const bool few = (int64_t)M * n_runs < (int64_t)sm_count() * 2 * kRowThreads * 3;
-  const int split = env_int("MMSBM_ROW_SPLIT", few ? 4 : 1);
-#define MMSBM_ROW_W_SPLIT(LDv)                                                                  \
-  if (LD == LDv && smem <= 200 * 1024 && split > 1) {                                           \
-    auto kern = row_w_split_kernel<LDv, 4>;                                                     \
-    const int per = kRowThreads / 4;                                                            \
-    const int gx = min((M + per - 1) / per, sm_count() * 4);                                    \
-    MMSBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<dim3(gx, n_runs), kRowThreads, smem, st>>>(own, pw, W, M, RNB);                      \
-    MMSBM_LAUNCH_CHECK("row_w_split_kernel");                                                   \
-    return 0;                                                                                   \
-  }
-  MMSBM_ROW_W_SPLIT(4) MMSBM_ROW_W_SPLIT(8) MMSBM_ROW_W_SPLIT(12) MMSBM_ROW_W_SPLIT(16) MMSBM_ROW_W_SPLIT(20)
-  MMSBM_ROW_W_SPLIT(24) MMSBM_ROW_W_SPLIT(28) MMSBM_ROW_W_SPLIT(32)
-#undef MMSBM_ROW_W_SPLIT
 #define MMSBM_ROW_W(LDv)                                                                        \
   if (LD == LDv && smem <= 200 * 1024) {                                                        \
     constexpr int kRows = (LDv <= 24) ? 2 : 1;   /* 2 x LD operand registers per lane */          \
@@ -840,21 +717,6 @@ int launch_n(const double* G, const double* pn, const double* own, const int32_t
   const size_t smem = (size_t)LD * RNB * 8;
   // one row per lane here: two rows cost occupancy (142 registers) and measured slower
   const int rows_env = env_int("MMSBM_ROWS_N", 1);
-  const bool few = (int64_t)M * n_runs < (int64_t)sm_count() * 2 * kRowThreads * 3;
-  const int split = env_int("MMSBM_ROW_SPLIT", few ? 4 : 1);
-#define MMSBM_ROW_N_SPLIT(LDv)                                                                  \
-  if (LD == LDv && smem <= 200 * 1024 && split > 1) {                                           \
-    auto kern = row_n_split_kernel<LDv, 4>;                                                     \
-    const int per = kRowThreads / 4;                                                            \
-    const int gx = min((M + per - 1) / per, sm_count() * 4);                                    \
-    MMSBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<dim3(gx, n_runs), kRowThreads, smem, st>>>(G, pn, own, deg, out, M, RNB, normalize); \
-    MMSBM_LAUNCH_CHECK("row_n_split_kernel");                                                   \
-    return 0;                                                                                   \
-  }
-  MMSBM_ROW_N_SPLIT(4) MMSBM_ROW_N_SPLIT(8) MMSBM_ROW_N_SPLIT(12) MMSBM_ROW_N_SPLIT(16) MMSBM_ROW_N_SPLIT(20)
-  MMSBM_ROW_N_SPLIT(24) MMSBM_ROW_N_SPLIT(28) MMSBM_ROW_N_SPLIT(32)
-#undef MMSBM_ROW_N_SPLIT
   // chunks in flight per lane: MMSBM_ROWN_PF (1 = round-1 behaviour); needs (RNB / 4) % PF == 0
   int pf = env_int("MMSBM_ROWN_PF", 5);
   if (pf != 1 && pf != 2 && pf != 5) pf = 1;
