@@ -577,7 +577,6 @@ static int launch_segment_pass_impl(SegArgs a, const double* nbr_pairs, const do
   PassShape sh = choose_shape(a.NBp, avg_degree);
   const int un_e = env_int("MMSBM_UN", 0), occ_e = env_int("MMSBM_OCC", 0);
   const RunPlan plan = plan_runs(a.NBp, n_runs, nbr_hexa != nullptr);
-  const bool pf = env_int("MMSBM_PREFETCH", 0) != 0;   // software-prefetch variants (seg_inst_pf.cu)
   const int single_from = plan.single_from;      // runs [single_from, n_runs) go one run per warp
   if (plan.hexas > 0) {
     const int hexas = plan.hexas;
@@ -591,8 +590,7 @@ static int launch_segment_pass_impl(SegArgs a, const double* nbr_pairs, const do
     const size_t smem = seg_smem_bytes(p, 6);
     MMSBM_REQUIRE(smem <= 227 * 1024, MMSBM_ERANGE, "segment pass needs %zu bytes of shared memory", smem);
     int rc = MMSBM_ERANGE;
-    if (pf) rc = launch_segment_pass_pf(p, sh.G, 3, 3, 6, dim3(gx, hexas), smem, st);
-    if (rc == MMSBM_ERANGE && (un_e > 0 || occ_e > 0))
+    if (un_e > 0 || occ_e > 0)
       rc = launch_segment_pass_hexa(p, sh.G, un_e > 0 ? un_e : 3, occ_e > 0 ? occ_e : 3, dim3(gx, hexas), smem, st);
     if (rc == MMSBM_ERANGE) rc = launch_segment_pass_hexa(p, sh.G, 3, 3, dim3(gx, hexas), smem, st);
     if (rc) {
@@ -616,8 +614,7 @@ static int launch_segment_pass_impl(SegArgs a, const double* nbr_pairs, const do
     MMSBM_REQUIRE(smem <= 227 * 1024, MMSBM_ERANGE, "segment pass needs %zu bytes of shared memory", smem);
     int UN = (sh.G == 1) ? 2 : 3, MINB = 3;                     // UN * (32 / 2G) <= 32
     int rc = MMSBM_ERANGE;
-    if (pf) rc = launch_segment_pass_pf(p, sh.G, UN, MINB, 2, dim3(gx, pairs), smem, st);
-    if (rc == MMSBM_ERANGE && (un_e > 0 || occ_e > 0))
+    if (un_e > 0 || occ_e > 0)
       rc = launch_segment_pass_pair(p, sh.G, un_e > 0 ? un_e : UN, occ_e > 0 ? occ_e : MINB, dim3(gx, pairs), smem, st);
     if (rc == MMSBM_ERANGE) rc = launch_segment_pass_pair(p, sh.G, UN, MINB, dim3(gx, pairs), smem, st);
     if (rc == MMSBM_ERANGE && sh.G == 1) rc = launch_segment_pass_pair(p, sh.G, 2, 3, dim3(gx, pairs), smem, st);
@@ -642,10 +639,6 @@ static int launch_segment_pass_impl(SegArgs a, const double* nbr_pairs, const do
       default: return launch_segment_pass_ch8(a, p.G, p.UN, p.MINB, grid, smem, st);
     }
   };
-  if (pf && sh.CH == 1) {
-    const int rc = launch_segment_pass_pf(a, sh.G, sh.UN, sh.MINB, 1, grid, smem, st);
-    if (rc != MMSBM_ERANGE) return rc;
-  }
   // tuning overrides (only combinations that were instantiated take effect)
   if (un_e > 0 || occ_e > 0) {
     PassShape alt = sh;

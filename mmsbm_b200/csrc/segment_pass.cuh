@@ -174,15 +174,7 @@ struct GroupSum {
 // runs are interleaved in memory, so a rating's gather is one contiguous 2*8*NB-byte read
 // (fewer L1 wavefronts per byte than two separate rows), and the index loads, the level
 // bookkeeping and the cross-group reductions are shared by the two runs.
-// PF == 1: software prefetch.  While a chunk is computed, the rows of the ratings SLOTS..2*SLOTS positions
-// ahead are requested into L1 (prefetch.global.L1, no destination register), so that by the time the
-// warp gets to them its 256-bit loads hit L1 instead of waiting for L2: loads in flight stop costing
-// registers.  One more coalesced id load and UN id shuffles + UN prefetches per chunk.
-__device__ __forceinline__ void prefetch_l1(const void* p) {
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-}
-
-template <int G, int CH, int UN, int MINB, int RUNS, int PF = 0>
+template <int G, int CH, int UN, int MINB, int RUNS>
 __global__ void __launch_bounds__(kWarps * 32, MINB)
 segment_pass_kernel(const SegArgs A) {
   constexpr int GR = G * RUNS;                   // lanes per rating
@@ -345,11 +337,6 @@ segment_pass_kernel(const SegArgs A) {
               const int nxt = base + cnt + lane;
               cur_ids = (lane < SLOTS && nxt < end) ? ld_stream(A.adj + nxt) : 0;
             }
-            int pf_ids = -1;                     // PF: ids one more chunk ahead (used after the arithmetic)
-            if constexpr (PF != 0) {
-              const int far = base + cnt + SLOTS + lane;
-              if (lane < SLOTS && far < end) pf_ids = ld_stream(A.adj + far);
-            }
             // all dots first, then the reciprocals, then the accumulation: every row is needed
             // by the first phase, so the loads are issued back to back
             double im[NS];
@@ -387,17 +374,6 @@ segment_pass_kernel(const SegArgs A) {
                 g[c].z = fma(x[un][c].z, im[un], g[c].z); g[c].w = fma(x[un][c].w, im[un], g[c].w);
               }
             }
-            if constexpr (PF != 0) {
-#pragma unroll
-              for (int un = 0; un < UN; ++un) {
-                const int id = __shfl_sync(kFull, pf_ids, (un * RPS + grp) & 31);
-                if (id >= 0 && lane_on) {
-#pragma unroll
-                  for (int c = 0; c < CH; ++c)
-                    if (con[c]) prefetch_l1(nbr_run + (size_t)id * (RUNS * NBp) + coff[c]);
-                }
-              }
-            }
           };
           static_assert(UN <= 6, "extend the step-count dispatch");
           const int ns = (cnt + RPS - 1) / RPS;  // steps that hold ratings, 1..UN (warp-uniform)
@@ -427,14 +403,11 @@ int launch_segment_pass_hexa(const SegArgs& a, int G, int UN, int MINB, dim3 gri
 int launch_segment_pass_ch2(const SegArgs& a, int G, int UN, int MINB, dim3 grid, size_t smem, cudaStream_t st);
 int launch_segment_pass_ch4(const SegArgs& a, int G, int UN, int MINB, dim3 grid, size_t smem, cudaStream_t st);
 int launch_segment_pass_ch8(const SegArgs& a, int G, int UN, int MINB, dim3 grid, size_t smem, cudaStream_t st);
-// the software-prefetch variants (PF = 1) of the shapes the BASELINE configurations use
-int launch_segment_pass_pf(const SegArgs& a, int G, int UN, int MINB, int RUNS, dim3 grid, size_t smem, cudaStream_t st);
 
 #define MMSBM_SEG_LAUNCH(Gv, CHv, UNv, MBv) MMSBM_SEG_LAUNCH_R(Gv, CHv, UNv, MBv, 1)
-#define MMSBM_SEG_LAUNCH_R(Gv, CHv, UNv, MBv, RUNSv) MMSBM_SEG_LAUNCH_P(Gv, CHv, UNv, MBv, RUNSv, 0, true)
-#define MMSBM_SEG_LAUNCH_P(Gv, CHv, UNv, MBv, RUNSv, PFv, cond)                                \
-  if (G == Gv && UN == UNv && MINB == MBv && (cond)) {                                         \
-    auto kern = segment_pass_kernel<Gv, CHv, UNv, MBv, RUNSv, PFv>;                            \
+#define MMSBM_SEG_LAUNCH_R(Gv, CHv, UNv, MBv, RUNSv)                                           \
+  if (G == Gv && UN == UNv && MINB == MBv) {                                                   \
+    auto kern = segment_pass_kernel<Gv, CHv, UNv, MBv, RUNSv>;                                 \
     MMSBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, dim3(kWarps * 32), smem, st>>>(a);                                            \
     MMSBM_LAUNCH_CHECK("segment_pass_kernel");                                                 \
