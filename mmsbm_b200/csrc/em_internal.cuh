@@ -34,7 +34,7 @@ int launch_n(const double* G, const double* pn, const double* own, const int32_t
              int M, int LD, int RNB, int normalize, int n_runs, cudaStream_t st);
 
 int launch_segment_pass_and_fixup(SegArgs a, const double* nbr_pairs, const double* nbr_hexa,
-                                  int64_t n_ratings, int n_runs, cudaStream_t st);
+                                  int64_t n_ratings, int n_runs, cudaStream_t st, bool no_long_segments = false);
 
 // n_pr from the side whose segments carry the accumulation: Acc = sum_seg own (x) g over `nseg`
 // segments (kPrSlabs partial sums, fixed order), x P, optionally normalised over the rating axis

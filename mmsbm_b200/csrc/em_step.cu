@@ -653,9 +653,10 @@ static int launch_segment_pass_impl(SegArgs a, const double* nbr_pairs, const do
 }
 
 int launch_segment_pass_and_fixup(SegArgs a, const double* nbr_pairs, const double* nbr_hexa,
-                                  int64_t n_ratings, int n_runs, cudaStream_t st) {
+                                  int64_t n_ratings, int n_runs, cudaStream_t st, bool no_long_segments) {
   int rc = launch_segment_pass_impl(a, nbr_pairs, nbr_hexa, n_ratings, n_runs, st);
   if (rc) return rc;
+  if (no_long_segments) return 0;               // the caller has read the schedule: nothing to add up
   const int64_t fix_ctas = 4 * sm_count();
   const unsigned gx = (unsigned)(a.lmax < fix_ctas ? a.lmax : fix_ctas);
   segment_fixup_kernel<<<dim3(gx, n_runs), 128, 0, st>>>(a);
@@ -850,6 +851,8 @@ extern "C" int mmsbm_em_workspace_bytes(int64_t N, int32_t U, int32_t I, int32_t
 // (w of the items, both n contractions): they are HBM-streaming while the segment passes are
 // bound by the L1/LSU pipe, so they overlap well.  Created per mmsbm_em_run call.
 struct Overlap {
+  // the caller read the two schedules: no segment is cut into pieces, the fix-up launches are skipped
+  bool no_long_u = false, no_long_i = false;
   cudaStream_t side = nullptr;
   cudaEvent_t e[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // Launch-bound sizes: the user side and the item side of an iteration only meet at the P tables,
@@ -921,7 +924,7 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
     {
       SegArgs a{useg, uadj, usched, eta, wg_u, slots_u, d.pmax_u, d.lmax, d.smax, U, I, d.ldl, R, 0, 0, 0,
                 dyn ? counters : nullptr};
-      if ((rc = launch_segment_pass_and_fixup(a, et2, et6, N, S, st))) return rc;
+      if ((rc = launch_segment_pass_and_fixup(a, et2, et6, N, S, st, ov->no_long_u))) return rc;
     }
     if ((rc = launch_n(wg_u, pn_u, theta, udeg, theta_out, U, d.ldk, d.rnb_u,
                        (flags & MMSBM_RAW_THETA) ? 0 : 1, S, st))) return rc;
@@ -932,7 +935,7 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
     {
       SegArgs a{iseg, iadj, isched, theta, wg_i, slots_i, d.pmax_i, d.lmax, d.smax, I, U, d.ldk, R, 0, 0, 0,
                 dyn ? counters + d.ctr_elems / 2 : nullptr};
-      if ((rc = launch_segment_pass_and_fixup(a, th2, nullptr, N, S, s2))) return rc;
+      if ((rc = launch_segment_pass_and_fixup(a, th2, nullptr, N, S, s2, ov->no_long_i))) return rc;
     }
     if ((rc = launch_n(wg_i, pn_i, eta, ideg, eta_out, I, d.ldl, d.rnb_i,
                        (flags & MMSBM_RAW_ETA_PR) ? 0 : 1, S, s2))) return rc;
@@ -959,7 +962,7 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
   {
     SegArgs a{useg, uadj, usched, eta, wg_u, slots_u, d.pmax_u, d.lmax, d.smax, U, I, d.ldl, R, 0, 0, 0,
               dyn ? counters : nullptr};
-    if ((rc = launch_segment_pass_and_fixup(a, et2, et6, N, S, st))) return rc;
+    if ((rc = launch_segment_pass_and_fixup(a, et2, et6, N, S, st, ov && ov->no_long_u))) return rc;
   }
   MMSBM_MARK(2);
   // theta' = (g x Pn) o theta / max(deg,1): off the critical path, overlaps the by-item pass
@@ -974,7 +977,7 @@ static int em_step_impl(const int32_t* useg, const int32_t* uadj, const int32_t*
     SegArgs a{iseg, iadj, isched, theta, wg_i, slots_i, d.pmax_i, d.lmax, d.smax, I, U, d.ldk, R, 0, 0, 0,
               dyn ? counters + d.ctr_elems / 2 : nullptr};
     // (pairs only: six interleaved theta tables of 138k users would not fit L2)
-    if ((rc = launch_segment_pass_and_fixup(a, th2, nullptr, N, S, st))) return rc;
+    if ((rc = launch_segment_pass_and_fixup(a, th2, nullptr, N, S, st, ov && ov->no_long_i))) return rc;
   }
   MMSBM_MARK(4);
   // eta' likewise; overlaps the pr kernels
@@ -1052,6 +1055,19 @@ extern "C" int mmsbm_em_run(const int32_t* useg, const int32_t* uadj, const int3
     MMSBM_CUDA(cudaStreamCreateWithFlags(&ov.side, cudaStreamNonBlocking));
     for (auto& e : ov.e) MMSBM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ov.two_branch = small && getenv("MMSBM_FORCE_OVERLAP") == nullptr;
+  }
+  {
+    // launch-bound sizes: read the headers of the two schedules once (16 bytes each; the only host
+    // synchronisation of the call) -- without long segments two launches per iteration go away
+    cudaStreamCaptureStatus cs0 = cudaStreamCaptureStatusNone;
+    if (small && iterations >= 8 && cudaStreamIsCapturing(st, &cs0) == cudaSuccess && cs0 == cudaStreamCaptureStatusNone) {
+      int32_t hu[4] = {0, 0, 1, 0}, hi[4] = {0, 0, 1, 0};
+      MMSBM_CUDA(cudaMemcpyAsync(hu, usched, sizeof(hu), cudaMemcpyDeviceToHost, st));
+      MMSBM_CUDA(cudaMemcpyAsync(hi, isched, sizeof(hi), cudaMemcpyDeviceToHost, st));
+      MMSBM_CUDA(cudaStreamSynchronize(st));
+      ov.no_long_u = hu[2] == 0;
+      ov.no_long_i = hi[2] == 0;
+    }
   }
   auto step = [&](bool fwd) {
     return em_step_impl(useg, uadj, udeg, iseg, iadj, ideg, usched, isched, N, U, I, R, K, L, S,
