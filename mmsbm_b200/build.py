@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmmsbm_b200.so")
-SOURCES = ["em_step.cu", "seg_inst_ch1.cu", "seg_inst_ch2.cu", "seg_inst_ch4.cu", "seg_inst_pair.cu", "seg_inst_hexa.cu", "graph_build.cu",
+SOURCES = ["em_step.cu", "em_small.cu", "seg_inst_ch1.cu", "seg_inst_ch2.cu", "seg_inst_ch4.cu", "seg_inst_pair.cu", "seg_inst_hexa.cu", "graph_build.cu",
            "reductions.cu", "host_api.cu", "sharded_run.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

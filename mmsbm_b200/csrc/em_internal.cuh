@@ -43,4 +43,13 @@ int launch_pr(const double* own, const double* g, double* partial, const double*
               bool normalize, cudaStream_t st);
 int launch_finalize_pr(double* pr, int kl_total, int R, cudaStream_t st);
 
+// em_small.cu: a whole fit of a small one-run problem in one cooperative launch.  Returns
+// MMSBM_ERANGE when the shape (or the device, or MMSBM_COOP=0) is not served: take the other path.
+bool em_small_applicable(int64_t N, int R, int K, int L, int S);
+size_t em_small_partial_elems(int R, int K);
+int launch_em_small(const int32_t* useg, const int32_t* uadj, const int32_t* udeg, const int32_t* iseg,
+                    const int32_t* iadj, const int32_t* ideg, int64_t N, int U, int I, int R, int K, int L, int S,
+                    int iterations, double* theta_a, double* eta_a, double* pr_a, double* theta_b, double* eta_b,
+                    double* pr_b, double* partial, size_t partial_elems, cudaStream_t st);
+
 }  // namespace mmsbm

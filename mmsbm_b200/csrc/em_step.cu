@@ -832,6 +832,12 @@ static EmDims em_dims(int64_t N, int U, int I, int R, int K, int L, int S) {
   return d;
 }
 
+static size_t em_main_bytes(const EmDims& d) {
+  return 4 * align_up(d.p_elems * 8) + align_up(d.wg_u_elems * 8) + align_up(d.wg_i_elems * 8) +
+         align_up(d.partial_elems * 8) + align_up(d.slots_u_elems * 8) + align_up(d.slots_i_elems * 8) +
+         align_up(d.th2_elems * 8) + align_up(d.et2_elems * 8) + align_up(d.et6_elems * 8) + align_up(d.ctr_elems * 4) + 256;
+}
+
 }  // namespace mmsbm
 
 using namespace mmsbm;
@@ -841,9 +847,9 @@ extern "C" int mmsbm_em_workspace_bytes(int64_t N, int32_t U, int32_t I, int32_t
   MMSBM_REQUIRE(bytes && N >= 0 && U > 0 && I > 0 && R > 0 && K > 0 && L > 0 && S > 0, MMSBM_EINVAL,
                 "mmsbm_em_workspace_bytes: bad argument");
   EmDims d = em_dims(N, U, I, R, K, L, S);
-  *bytes = 4 * align_up(d.p_elems * 8) + align_up(d.wg_u_elems * 8) + align_up(d.wg_i_elems * 8) +
-           align_up(d.partial_elems * 8) + align_up(d.slots_u_elems * 8) + align_up(d.slots_i_elems * 8) +
-           align_up(d.th2_elems * 8) + align_up(d.et2_elems * 8) + align_up(d.et6_elems * 8) + align_up(d.ctr_elems * 4) + 256;
+  *bytes = em_main_bytes(d);
+  // the cooperative small-problem path (em_small.cu) keeps one partial n_pr per CTA behind the rest
+  if (em_small_applicable(N, R, K, L, S)) *bytes += align_up(em_small_partial_elems(R, K) * 8);
   return 0;
 }
 
@@ -1048,6 +1054,18 @@ extern "C" int mmsbm_em_run(const int32_t* useg, const int32_t* uadj, const int3
                             size_t ws_bytes, void* stream) {
   MMSBM_REQUIRE(iterations >= 0, MMSBM_EINVAL, "mmsbm_em_run: negative iteration count");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // small one-run problems: the whole loop in one cooperative launch (em_small.cu)
+  if (iterations > 0 && N >= 0 && U > 0 && I > 0 && R > 0 && K > 0 && L > 0 && em_small_applicable(N, R, K, L, S) &&
+      useg && uadj && udeg && iseg && iadj && ideg && theta_a && eta_a && pr_a && theta_b && eta_b && pr_b && ws) {
+    const size_t main_bytes = em_main_bytes(em_dims(N, U, I, R, K, L, S));
+    const size_t part_elems = em_small_partial_elems(R, K);
+    if (ws_bytes >= main_bytes + part_elems * 8) {
+      const int rc = launch_em_small(useg, uadj, udeg, iseg, iadj, ideg, N, U, I, R, K, L, S, iterations, theta_a,
+                                     eta_a, pr_a, theta_b, eta_b, pr_b,
+                                     reinterpret_cast<double*>(static_cast<char*>(ws) + main_bytes), part_elems, st);
+      if (rc != MMSBM_ERANGE) return rc;
+    }
+  }
   Overlap ov;
   const bool small = (double)N * S < 5.0e7;
   const bool overlap = iterations > 0 && getenv("MMSBM_NO_OVERLAP") == nullptr;

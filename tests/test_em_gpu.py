@@ -755,3 +755,54 @@ def test_one_sided_build_equals_a_slice_of_the_full_index():
     for off, cnt in ((4, a[0]), (4 + pmax, a[0]), (4 + 2 * pmax, a[0]), (4 + 3 * pmax, a[2]),
                      (4 + 3 * pmax + lmax, a[2] + 1)):       # the filled part of each table
         np.testing.assert_array_equal(a[off:off + cnt], b[off:off + cnt])
+
+
+# ------------------------------------------------------------- small one-run problems: one cooperative launch
+@pytest.mark.parametrize("U,I,N,K,L,R,heavy,T", [
+    (943, 1682, 100_000, 10, 10, 5, False, 7),       # the ML-100K shape
+    (300, 200, 20_000, 10, 10, 5, True, 4),          # heavy-tailed: segments > 1024 ratings take the CTA-wide walk
+    (5, 10, 100, 2, 2, 5, False, 10),                # the reference fixture's shape (4-double rows, one lane per row)
+    (400, 900, 30_000, 7, 8, 4, True, 3),            # 8-double rows, K != L inside one stride
+    (50, 40, 3000, 12, 9, 8, False, 1),              # eight rating levels, a single iteration
+    (700, 30, 40_000, 3, 4, 3, True, 5),             # more users than items and the reverse below: either side emits n_pr
+    (30, 700, 40_000, 4, 3, 3, True, 6),
+])
+def test_cooperative_small_path_vs_oracle(U, I, N, K, L, R, heavy, T, monkeypatch):
+    """mmsbm_em_run takes one-run problems with rows of at most 12 doubles through em_small.cu (the
+    whole loop in one cooperative launch).  T iterations against the oracle's loop (1e-10 per element
+    per iteration would allow T * 1e-10; observed ~1e-14), likelihood within 1e-8, ids without any
+    rating keep zero rows, and the multi-kernel path (MMSBM_COOP=0) agrees to rounding."""
+    from mmsbm_b200 import _lib
+    from mmsbm_b200.engine import Engine
+    data = random_triples(101, N, U, I, R, heavy_tail=heavy)
+    data = data[data[:, 0] != 1]                              # user 1 has no rating at all
+    theta, eta, pr = random_params(103, U, I, K, L, R, S=1)
+    fu, fi = orc.degree_factors(np.vstack([data, [[U - 1, I - 1, R - 1]]]), K, L)
+    fu[1] = 1
+    outs = {}
+    for coop in ("1", "0"):
+        monkeypatch.setenv("MMSBM_COOP", coop)
+        l0 = _lib.launch_count()
+        e = Engine(data, U, I, R, K, L)
+        e.set_params(theta, eta, pr)
+        l1 = _lib.launch_count()
+        e.run(T)
+        launches = _lib.launch_count() - l1
+        outs[coop] = e.get_params() + (e.likelihood(),)
+        if coop == "1":
+            assert launches == 1, launches                   # ONE kernel for all T iterations
+        else:
+            assert launches > T
+        del l0
+    t, et, p = theta[0], eta[0], pr[0]
+    for _ in range(T):
+        t, et, p = orc.em_iteration(data, t, et, p, fu, fi)
+    want_lik = orc.likelihood(data, t, et, p)
+    for coop, (gt, ge, gp, glik) in outs.items():
+        errs = (rel_err(gt[0], t), rel_err(ge[0], et), rel_err(gp[0], p))
+        print(f"coop={coop} U={U} I={I} K={K} L={L} R={R}: rel err after {T} iterations {errs}")
+        assert max(errs) < PARAM_TOL * T
+        assert abs(glik[0] - want_lik) <= LIK_TOL * abs(want_lik)
+        assert np.all(gt[0][1] == 0.0)
+    for a, b in zip(outs["1"][:3], outs["0"][:3]):
+        assert rel_err(a, b) < 1e-11
