@@ -64,11 +64,11 @@ __device__ __forceinline__ double p_at(const double* Ps, int LD, int side, int r
 }
 
 template <int LD>
-__global__ void __launch_bounds__(kSmallWarps * 32) em_small_kernel(const SmallArgs A) {
+__global__ void __launch_bounds__(kSmallWarps * 32, 2) em_small_kernel(const SmallArgs A) {
   cg::grid_group grid = cg::this_grid();
   constexpr int G = LD / 4;                     // lanes per neighbour row
   constexpr int RPS = 32 / G;                   // ratings per step
-  constexpr int UN = (G == 1) ? 1 : 2;          // steps per chunk (UN * RPS <= 32 ids per chunk)
+  constexpr int UN = (G == 1) ? 1 : (G == 2) ? 2 : 3;   // steps per chunk (UN * RPS <= 32 ids per chunk)
   constexpr int SLOTS = UN * RPS;
   constexpr int MAXE = (kSmallMaxR * LD * LD + 31) / 32;
   const int R = A.R, NE = R * LD * LD, RLD = R * LD;
@@ -199,6 +199,15 @@ __global__ void __launch_bounds__(kSmallWarps * 32) em_small_kernel(const SmallA
     __syncwarp();
   };
 
+  // does any segment of this CTA need the CTA-wide walk?  (if not, its warps never wait for each other)
+  const int stride = gridDim.x * kSmallWarps;
+  int mine_long = 0;
+  for (int s = blockIdx.x + (int)threadIdx.x * (int)gridDim.x; s < nseg; s += (int)blockDim.x * (int)gridDim.x) {
+    const int sd = s >= A.n[0] ? 1 : 0;
+    if (__ldg(A.deg[sd] + (sd ? s - A.n[0] : s)) > kSmallLong) mine_long = 1;
+  }
+  const bool cta_has_long = __syncthreads_or(mine_long) != 0;
+
   for (int it = 0; it < A.iterations; ++it) {
     const int cur = it & 1, nxt = cur ^ 1;
     for (int e = threadIdx.x; e < NE; e += blockDim.x) {     // P of this iteration, zero padded
@@ -210,7 +219,14 @@ __global__ void __launch_bounds__(kSmallWarps * 32) em_small_kernel(const SmallA
     __syncthreads();
 
     // ---- the segments of this CTA, one per warp and round ----
-    const int stride = gridDim.x * kSmallWarps;
+    if (!cta_has_long) {                                     // the common case: every warp walks its own list
+      for (int s = blockIdx.x + warp * (int)gridDim.x; s < nseg; s += stride) {
+        const int side = s >= A.n[0] ? 1 : 0, id = side ? s - A.n[0] : s;
+        load_own_and_w(side, id, cur);
+        stream_levels(side, id, cur, 0, 1);
+        epilogue(side, id, nxt);
+      }
+    } else
     for (int s0 = blockIdx.x; s0 < nseg; s0 += stride) {     // CTA-uniform round loop
       const int s = s0 + warp * gridDim.x;
       const bool have = s < nseg;

@@ -777,8 +777,8 @@ def test_cooperative_small_path_vs_oracle(U, I, N, K, L, R, heavy, T, monkeypatc
     data = random_triples(101, N, U, I, R, heavy_tail=heavy)
     data = data[data[:, 0] != 1]                              # user 1 has no rating at all
     theta, eta, pr = random_params(103, U, I, K, L, R, S=1)
-    fu, fi = orc.degree_factors(np.vstack([data, [[U - 1, I - 1, R - 1]]]), K, L)
-    fu[1] = 1
+    fu = np.repeat(np.maximum(np.bincount(data[:, 0], minlength=U), 1)[:, None], K, axis=1)
+    fi = np.repeat(np.maximum(np.bincount(data[:, 1], minlength=I), 1)[:, None], L, axis=1)
     outs = {}
     for coop in ("1", "0"):
         monkeypatch.setenv("MMSBM_COOP", coop)
