@@ -48,8 +48,9 @@ int launch_finalize_pr(double* pr, int kl_total, int R, cudaStream_t st);
 bool em_small_applicable(int64_t N, int R, int K, int L, int S);
 size_t em_small_partial_elems(int R, int K);
 int launch_em_small(const int32_t* useg, const int32_t* uadj, const int32_t* udeg, const int32_t* iseg,
-                    const int32_t* iadj, const int32_t* ideg, int64_t N, int U, int I, int R, int K, int L, int S,
-                    int iterations, double* theta_a, double* eta_a, double* pr_a, double* theta_b, double* eta_b,
-                    double* pr_b, double* partial, size_t partial_elems, cudaStream_t st);
+                    const int32_t* iadj, const int32_t* ideg, const int32_t* usched, const int32_t* isched, int64_t N,
+                    int U, int I, int R, int K, int L, int S, int iterations, double* theta_a, double* eta_a,
+                    double* pr_a, double* theta_b, double* eta_b, double* pr_b, double* partial, size_t partial_elems,
+                    cudaStream_t st);
 
 }  // namespace mmsbm

@@ -33,7 +33,7 @@ namespace cg = cooperative_groups;
 
 namespace mmsbm {
 
-constexpr int kSmallWarps = 8;
+constexpr int kSmallWarps = 12;     // per CTA, one CTA per SM: 170 registers per thread
 constexpr int kSmallLong = 1024;      // longer segments are walked by a whole CTA
 constexpr int kSmallMaxR = 8;
 
@@ -64,30 +64,28 @@ __device__ __forceinline__ double p_at(const double* Ps, int LD, int side, int r
 }
 
 template <int LD>
-__global__ void __launch_bounds__(kSmallWarps * 32, 2) em_small_kernel(const SmallArgs A) {
+__global__ void __launch_bounds__(kSmallWarps * 32, 1) em_small_kernel(const SmallArgs A) {
   cg::grid_group grid = cg::this_grid();
   constexpr int G = LD / 4;                     // lanes per neighbour row
   constexpr int RPS = 32 / G;                   // ratings per step
   constexpr int UN = (G == 1) ? 1 : (G == 2) ? 2 : 3;   // steps per chunk (UN * RPS <= 32 ids per chunk)
   constexpr int SLOTS = UN * RPS;
-  constexpr int MAXE = (kSmallMaxR * LD * LD + 31) / 32;
   const int R = A.R, NE = R * LD * LD, RLD = R * LD;
 
   extern __shared__ __align__(32) unsigned char smem_raw[];
   double* Ps = reinterpret_cast<double*>(smem_raw);          // [R][LD][LD]
-  double* cta_acc = Ps + NE;                                 // [NE]
-  double* warp_area = cta_acc + NE;                          // per warp: own_s[LD] | w_s[R*LD] | g_s[R*LD]
+  double* warp_area = Ps + NE;              // per warp: own_s[LD] | w_s[R*LD] | g_s[R*LD] | acc_s[NE] (n_pr accumulators)
   __shared__ int long_side[kSmallWarps], long_id[kSmallWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int per_warp = LD + 2 * RLD;
+  const int per_warp = LD + 2 * RLD + NE;
   double* own_s = warp_area + (size_t)warp * per_warp;
   double* w_s = own_s + LD;
   double* g_s = w_s + RLD;
+  double* acc_s = g_s + RLD;
   const int grp = lane / G, q = lane - grp * G;
   const bool lane_on = grp < RPS;
   const GroupSum<G> group_sum(grp * G, q);
   const int nseg = A.n[0] + A.n[1];
-  double acc[MAXE];
 
   // own row and w = own x P of segment (side, id) into this warp's shared memory
   auto load_own_and_w = [&](int side, int id, int cur) {
@@ -187,13 +185,9 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 2) em_small_kernel(const Sma
       A.own[side][nxt][(size_t)id * LD + lane] = v;
     }
     if (side == A.emit_side) {
-#pragma unroll
-      for (int j = 0; j < MAXE; ++j) {
-        const int e = lane + 32 * j;
-        if (e < NE) {
-          const int r = e / (LD * LD), k = (e / LD) % LD, l = e % LD;
-          acc[j] = side == 0 ? fma(own_s[k], g_s[r * LD + l], acc[j]) : fma(own_s[l], g_s[r * LD + k], acc[j]);
-        }
+      for (int e = lane; e < NE; e += 32) {
+        const int r = e / (LD * LD), k = (e / LD) % LD, l = e % LD;
+        acc_s[e] = side == 0 ? fma(own_s[k], g_s[r * LD + l], acc_s[e]) : fma(own_s[l], g_s[r * LD + k], acc_s[e]);
       }
     }
     __syncwarp();
@@ -214,8 +208,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 2) em_small_kernel(const Sma
       const int r = e / (LD * LD), k = (e / LD) % LD, l = e % LD;
       Ps[e] = (k < A.K && l < A.L) ? A.pr[cur][((size_t)k * A.L + l) * R + r] : 0.0;
     }
-#pragma unroll
-    for (int j = 0; j < MAXE; ++j) acc[j] = 0.0;
+    for (int e = lane; e < NE; e += 32) acc_s[e] = 0.0;
     __syncthreads();
 
     // ---- the segments of this CTA, one per warp and round ----
@@ -255,7 +248,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 2) em_small_kernel(const Sma
         if (warp == 0) {                                     // partial g rows added in warp order
           for (int v = lane; v < RLD; v += 32) {
             double t = g_s[v];
-            for (int ww = 1; ww < kSmallWarps; ++ww) t += warp_area[(size_t)ww * per_warp + LD + RLD + v];
+            for (int ww = 1; ww < kSmallWarps; ++ww) t += warp_area[(size_t)ww * per_warp + LD + RLD + v];   // g_s of warp ww
             g_s[v] = t;
           }
           __syncwarp();
@@ -267,19 +260,12 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 2) em_small_kernel(const Sma
     }
 
     // ---- n_pr: accumulators of the warps added in warp order, one partial per CTA ----
-    for (int e = threadIdx.x; e < NE; e += blockDim.x) cta_acc[e] = 0.0;
     __syncthreads();
-    for (int w = 0; w < kSmallWarps; ++w) {
-      if (warp == w) {
-#pragma unroll
-        for (int j = 0; j < MAXE; ++j) {
-          const int e = lane + 32 * j;
-          if (e < NE) cta_acc[e] += acc[j];
-        }
-      }
-      __syncthreads();
+    for (int e = threadIdx.x; e < NE; e += blockDim.x) {
+      double t = 0.0;
+      for (int w = 0; w < kSmallWarps; ++w) t += warp_area[(size_t)w * per_warp + LD + 2 * RLD + e];
+      A.partial[(size_t)blockIdx.x * NE + e] = t;
     }
-    for (int e = threadIdx.x; e < NE; e += blockDim.x) A.partial[(size_t)blockIdx.x * NE + e] = cta_acc[e];
     grid.sync();
 
     // ---- pr' = P o (sum over the CTAs), normalised over the rating axis: one warp per (k, l) ----
@@ -306,12 +292,12 @@ template <int LD>
 static int launch_small(const SmallArgs& a, int ctas_wanted, cudaStream_t st) {
   auto kern = em_small_kernel<LD>;
   const int NE = a.R * LD * LD;
-  const size_t smem = ((size_t)2 * NE + (size_t)kSmallWarps * (LD + 2 * a.R * LD)) * 8;
+  const size_t smem = ((size_t)NE + (size_t)kSmallWarps * (LD + 2 * a.R * LD + NE)) * 8;
   MMSBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   MMSBM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSmallWarps * 32, smem));
   if (per_sm < 1) return MMSBM_ERANGE;
-  if (per_sm > 2) per_sm = 2;
+  if (per_sm > 1) per_sm = 1;
   int grid = per_sm * sm_count();
   if (grid > ctas_wanted) grid = ctas_wanted;
   if (grid < 1) grid = 1;
@@ -333,9 +319,10 @@ size_t em_small_partial_elems(int R, int K) { return (size_t)512 * R * row_strid
 
 // MMSBM_ERANGE: shape not served by this path (the caller takes the multi-kernel path)
 int launch_em_small(const int32_t* useg, const int32_t* uadj, const int32_t* udeg, const int32_t* iseg,
-                    const int32_t* iadj, const int32_t* ideg, int64_t N, int U, int I, int R, int K, int L, int S,
-                    int iterations, double* theta_a, double* eta_a, double* pr_a, double* theta_b, double* eta_b,
-                    double* pr_b, double* partial, size_t partial_elems, cudaStream_t st) {
+                    const int32_t* iadj, const int32_t* ideg, const int32_t* usched, const int32_t* isched, int64_t N,
+                    int U, int I, int R, int K, int L, int S, int iterations, double* theta_a, double* eta_a,
+                    double* pr_a, double* theta_b, double* eta_b, double* pr_b, double* partial, size_t partial_elems,
+                    cudaStream_t st) {
   const int ldk = row_stride(K);
   if (!em_small_applicable(N, R, K, L, S) || iterations <= 0 || !partial) return MMSBM_ERANGE;
   if (env_int("MMSBM_COOP", 1) == 0) return MMSBM_ERANGE;
@@ -345,6 +332,17 @@ int launch_em_small(const int32_t* useg, const int32_t* uadj, const int32_t* ude
     return MMSBM_ERANGE;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return MMSBM_ERANGE;
+  {
+    // a segment of more than MMSBM_PIECE_LEN ratings (heavy-tailed ids) would be walked by one CTA while the
+    // rest of the grid waits at the barrier: such problems stay on the multi-kernel path, whose piece
+    // schedule spreads the segment over the GPU.  The schedule headers say whether one exists (16 bytes
+    // each; the only host synchronisation of the call)
+    int32_t hu[4] = {0, 0, 1, 0}, hi[4] = {0, 0, 1, 0};
+    MMSBM_CUDA(cudaMemcpyAsync(hu, usched, sizeof(hu), cudaMemcpyDeviceToHost, st));
+    MMSBM_CUDA(cudaMemcpyAsync(hi, isched, sizeof(hi), cudaMemcpyDeviceToHost, st));
+    MMSBM_CUDA(cudaStreamSynchronize(st));
+    if (hu[2] != 0 || hi[2] != 0) return MMSBM_ERANGE;
+  }
   SmallArgs a{};
   a.seg[0] = useg; a.seg[1] = iseg; a.adj[0] = uadj; a.adj[1] = iadj; a.deg[0] = udeg; a.deg[1] = ideg;
   a.own[0][0] = theta_a; a.own[0][1] = theta_b; a.own[1][0] = eta_a; a.own[1][1] = eta_b;

@@ -1056,12 +1056,13 @@ extern "C" int mmsbm_em_run(const int32_t* useg, const int32_t* uadj, const int3
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // small one-run problems: the whole loop in one cooperative launch (em_small.cu)
   if (iterations > 0 && N >= 0 && U > 0 && I > 0 && R > 0 && K > 0 && L > 0 && em_small_applicable(N, R, K, L, S) &&
-      useg && uadj && udeg && iseg && iadj && ideg && theta_a && eta_a && pr_a && theta_b && eta_b && pr_b && ws) {
+      useg && uadj && udeg && iseg && iadj && ideg && usched && isched && theta_a && eta_a && pr_a && theta_b &&
+      eta_b && pr_b && ws) {
     const size_t main_bytes = em_main_bytes(em_dims(N, U, I, R, K, L, S));
     const size_t part_elems = em_small_partial_elems(R, K);
     if (ws_bytes >= main_bytes + part_elems * 8) {
-      const int rc = launch_em_small(useg, uadj, udeg, iseg, iadj, ideg, N, U, I, R, K, L, S, iterations, theta_a,
-                                     eta_a, pr_a, theta_b, eta_b, pr_b,
+      const int rc = launch_em_small(useg, uadj, udeg, iseg, iadj, ideg, usched, isched, N, U, I, R, K, L, S,
+                                     iterations, theta_a, eta_a, pr_a, theta_b, eta_b, pr_b,
                                      reinterpret_cast<double*>(static_cast<char*>(ws) + main_bytes), part_elems, st);
       if (rc != MMSBM_ERANGE) return rc;
     }

@@ -760,7 +760,8 @@ def test_one_sided_build_equals_a_slice_of_the_full_index():
 # ------------------------------------------------------------- small one-run problems: one cooperative launch
 @pytest.mark.parametrize("U,I,N,K,L,R,heavy,T", [
     (943, 1682, 100_000, 10, 10, 5, False, 7),       # the ML-100K shape
-    (300, 200, 20_000, 10, 10, 5, True, 4),          # heavy-tailed: segments > 1024 ratings take the CTA-wide walk
+    (300, 200, 10_000, 10, 10, 5, True, 4),          # heavy-tailed: the top segments (1024 < ratings <= 2048) take the CTA-wide walk
+    (300, 200, 40_000, 10, 10, 5, True, 4),          # a segment of > 2048 ratings: stays on the multi-kernel path
     (5, 10, 100, 2, 2, 5, False, 10),                # the reference fixture's shape (4-double rows, one lane per row)
     (400, 900, 30_000, 7, 8, 4, True, 3),            # 8-double rows, K != L inside one stride
     (50, 40, 3000, 12, 9, 8, False, 1),              # eight rating levels, a single iteration
@@ -768,8 +769,8 @@ def test_one_sided_build_equals_a_slice_of_the_full_index():
     (30, 700, 40_000, 4, 3, 3, True, 6),
 ])
 def test_cooperative_small_path_vs_oracle(U, I, N, K, L, R, heavy, T, monkeypatch):
-    """mmsbm_em_run takes one-run problems with rows of at most 12 doubles through em_small.cu (the
-    whole loop in one cooperative launch).  T iterations against the oracle's loop (1e-10 per element
+    """mmsbm_em_run takes one-run problems with rows of at most 12 doubles and no segment beyond
+    2048 ratings through em_small.cu (the whole loop in one cooperative launch).  T iterations against the oracle's loop (1e-10 per element
     per iteration would allow T * 1e-10; observed ~1e-14), likelihood within 1e-8, ids without any
     rating keep zero rows, and the multi-kernel path (MMSBM_COOP=0) agrees to rounding."""
     from mmsbm_b200 import _lib
@@ -789,10 +790,13 @@ def test_cooperative_small_path_vs_oracle(U, I, N, K, L, R, heavy, T, monkeypatc
         e.run(T)
         launches = _lib.launch_count() - l1
         outs[coop] = e.get_params() + (e.likelihood(),)
-        if coop == "1":
+        top = max(np.bincount(data[:, 0]).max(), np.bincount(data[:, 1]).max())
+        if coop == "1" and top <= 2048:
             assert launches == 1, launches                   # ONE kernel for all T iterations
         else:
             assert launches > T
+        if (U, N) == (300, 10_000):
+            assert 1024 < top <= 2048
         del l0
     t, et, p = theta[0], eta[0], pr[0]
     for _ in range(T):
