@@ -378,14 +378,14 @@ def kernel_times(eng, lib, _lib, shape, reps=5):
             "n_items": float(k[4]), "pr": float(k[5] + k[6])}
 
 
-def roofline_block(workload, shape, k_ms, ms_per_iteration):
+def roofline_block(workload, shape, k_ms, ms_per_iteration, use_record=True):
     """See the module docstring.  Every fraction is (measured bytes) / (measured time) / (measured
     peak); the ncu record and the peaks file are named so that each can be recomputed."""
     U, I, N, K, L, S = shape
     ldk, ldl = 4 * ((K + 3) // 4), 4 * ((L + 3) // 4)
     peak, peak_src = hbm_peak()
     seg_ms = k_ms["by_user"] + k_ms["by_item"]
-    rec = (_json(os.path.join(ROOT, "profiles", "ncu_records.json")) or {}).get(workload)
+    rec = (_json(os.path.join(ROOT, "profiles", "ncu_records.json")) or {}).get(workload) if use_record else None
     peaks = _json(os.path.join(ROOT, "profiles", "peaks.json")) or {}
     out = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
            "peak_source": peak_src, "kernel": "segment_pass_kernel (by-user + by-item launches of one iteration)",
@@ -505,7 +505,13 @@ def run_single(args, shape, cx):
     ms_it = ms / args.steps / T
 
     k_ms = kernel_times(eng, lib, _lib, shape)
-    roofline = roofline_block(args.workload, shape, k_ms, ms_it)
+    cooperative = launches == args.steps        # one launch per fit: the small-problem kernel (em_small.cu)
+    roofline = roofline_block(args.workload, shape, k_ms, ms_it, use_record=not cooperative)
+    if cooperative:
+        roofline["kernel"] = ("em_small_kernel: the whole fit is ONE cooperative launch (two grid barriers per "
+                              "iteration); latency-bound, no bandwidth fraction applies. kernel_ms / gather are the "
+                              "stages of the multi-kernel step (mmsbm_em_step), for reference only")
+        roofline["binding_resource"] = "latency of the dependent chain inside an iteration (grid barriers, L2 round trips)"
 
     # ---- end to end through the host-pointer C ABI ----
     e2e = verify = None
