@@ -138,9 +138,13 @@ int mmsbm_em_step_profiled(const int32_t* useg_dev, const int32_t* uadj_dev, con
                            double* theta_out_dev, double* eta_out_dev, double* pr_out_dev,
                            int32_t flags, void* workspace_dev, size_t workspace_bytes, void* stream,
                            float* ms7);
-/* ``iterations`` steps ping-ponging between (theta,eta,pr)_a and _b, no host sync;
- * the result is in the _a buffers when iterations is even, else in _b.
- * Replaces the loop src/mmsbm.py:243-250. */
+/* ``iterations`` steps ping-ponging between (theta,eta,pr)_a and _b; the result is in the _a buffers
+ * when iterations is even, else in _b.  Replaces the loop src/mmsbm.py:243-250.  Asynchronous on
+ * ``stream``, with one exception: for launch-bound sizes (n_ratings * n_runs < 5e7) the call first
+ * reads the 16-byte headers of the two schedules (one stream synchronisation) to choose its launch
+ * strategy -- the two-branch CUDA graph of csrc/em_step.cu, or, for one run with rows of at most 12
+ * doubles and no segment beyond MMSBM_PIECE_LEN ratings, the single cooperative launch of
+ * csrc/em_small.cu that runs the whole loop inside one kernel. */
 int mmsbm_em_run(const int32_t* useg_dev, const int32_t* uadj_dev, const int32_t* udeg_dev,
                  const int32_t* iseg_dev, const int32_t* iadj_dev, const int32_t* ideg_dev,
                  const int32_t* usched_dev, const int32_t* isched_dev,

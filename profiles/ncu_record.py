@@ -19,7 +19,8 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1e-6, 
         "second": 1e3, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}          # times in ms, sizes in bytes
 
 
-def main(path, workload, source):
+def extract(path, source=None):
+    """The per-iteration record of one metrics CSV (see the module docstring)."""
     lines = open(path).read().splitlines()
     start = next(i for i, l in enumerate(lines) if l.startswith('"ID"'))
     launches = collections.OrderedDict()
@@ -49,13 +50,18 @@ def main(path, workload, source):
     for d in it:
         k = per_kernel.setdefault(d["name"].replace("void ", "").replace("mmsbm::", ""), {"launches": 0, "ms": 0.0, "dram_bytes": 0.0})
         k["launches"] += 1; k["ms"] += d.get(M_T, 0.0); k["dram_bytes"] += d.get(M_R, 0.0) + d.get(M_W, 0.0)
-    rec = {"source": source, "iterations_seen": len(cut), "launches_per_iteration": len(it),
+    rec = {"source": source or path, "iterations_seen": len(cut), "launches_per_iteration": len(it),
            "dram_bytes_per_iteration": dram(it), "segment_pass_dram_bytes": dram(seg),
            "l1_global_load_bytes_per_iteration": sum(d.get(M_L1, 0.0) for d in it) * 32.0,
            "ncu_ms_per_iteration": sum(d.get(M_T, 0.0) for d in it),
            "segment_pass_share_of_ncu_time": sum(d.get(M_T, 0.0) for d in seg) / sum(d.get(M_T, 0.0) for d in it),
            "fp64_pipe_pct": tw(seg, M_F64), "l2_hit_pct": tw(seg, M_L2), "lsu_pipe_pct": tw(seg, M_LSU) or None,
            "per_kernel": per_kernel}
+    return rec
+
+
+def main(path, workload, source):
+    rec = extract(path, source)
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_records.json")
     allrec = json.load(open(out)) if os.path.exists(out) else {}
     allrec[workload] = rec

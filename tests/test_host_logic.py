@@ -252,3 +252,40 @@ def test_bench_algorithmic_bytes_match_the_survey_table():
     for name, want_b in want.items():
         U, I, N, K, L, S = bench.WORKLOADS[name]
         assert abs(bench.b_alg(U, I, N, K, L, S) - want_b) < 0.06, name
+
+
+def test_committed_roofline_fractions_are_physical_and_reproducible():
+    """Every fraction of the roofline block of a committed bench line can be recomputed from files
+    under profiles/ -- the ncu metrics CSV named in the line (re-parsed here), the peaks file, the
+    line's own times -- and none exceeds 1."""
+    import glob
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("ncu_record", os.path.join(root, "profiles", "ncu_record.py"))
+    ncu_record = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ncu_record)
+    peaks = json.load(open(os.path.join(root, "profiles", "peaks.json")))
+    seen = 0
+    for path in sorted(glob.glob(os.path.join(root, "profiles", "r2_v1[5-9]_bench_*.json"))):
+        line = json.loads(open(path).read().strip().splitlines()[-1])
+        roof = line.get("roofline")
+        if not roof or line.get("n_gpus") != 1 or line.get("impl") == "reference":
+            continue
+        g = roof["gather"]
+        seg_ms = roof["kernel_ms"]["by_user"] + roof["kernel_ms"]["by_item"]
+        assert g["peak_gbs"] == peaks["gather_gbs"]
+        assert abs(g["achieved_gbs"] - g["bytes_per_iteration"] / (seg_ms * 1e-3) / 1e9) < 1e-6 * g["achieved_gbs"]
+        assert 0.0 < g["frac"] <= 1.0
+        if roof["frac"] is None:
+            continue                                         # cooperative path: no bandwidth fraction claimed
+        src = os.path.join(root, roof["ncu_record"])
+        assert os.path.exists(src), f"{path} names {roof['ncu_record']}, which is not committed"
+        rec = ncu_record.extract(src)
+        want = rec["dram_bytes_per_iteration"] / (line["ms_per_iteration"] * 1e-3) / 1e9
+        assert abs(roof["achieved"] - want) < 1e-6 * want
+        assert abs(roof["frac"] - want / roof["peak"]) < 1e-9
+        assert 0.0 < roof["frac"] <= 1.0
+        assert abs(roof["traffic"] - rec["segment_pass_dram_bytes"]) < 1e-6 * roof["traffic"]
+        assert roof["traffic"] <= rec["dram_bytes_per_iteration"]
+        seen += 1
+    assert seen >= 3
