@@ -134,22 +134,10 @@ class Engine:
             raise ValueError("parameter shapes do not match the engine")
         dev = self.device
         self.S = S
-        # eta and pr of a buffer set share one allocation, so that the rating-sharded exchange
-        # (parallel.RatingShardedEngine) all-reduces both with a single collective and no copy
-        def pair(eta_np, pr_np):
-            n_eta = S * self.I * self.ldl
-            flat = torch.empty(n_eta + S * self.K * self.L * self.R, dtype=torch.float64, device=dev)
-            eta_t = flat[:n_eta].view(S, self.I, self.ldl)
-            pr_t = flat[n_eta:].view(S, self.K, self.L, self.R)
-            if eta_np is not None:
-                eta_t.copy_(torch.from_numpy(self._pad(eta_np, self.ldl)))
-                pr_t.copy_(torch.from_numpy(np.ascontiguousarray(pr_np, dtype=np.float64)))
-            return flat, eta_t, pr_t
         self.theta = torch.from_numpy(self._pad(theta, self.ldk)).to(dev)
-        self._flat, self.eta, self.pr = pair(eta, pr)
-        alt_flat, alt_eta, alt_pr = pair(None, None)
-        self._alt = (torch.empty_like(self.theta), alt_eta, alt_pr)
-        self._alt_flat = alt_flat
+        self.eta = torch.from_numpy(self._pad(eta, self.ldl)).to(dev)
+        self.pr = torch.from_numpy(np.ascontiguousarray(pr, dtype=np.float64)).to(dev)
+        self._alt = (torch.empty_like(self.theta), torch.empty_like(self.eta), torch.empty_like(self.pr))
         if getattr(self, "useg", None) is None:   # prediction-only engine: no EM workspace
             self._ws, self._ws_bytes = None, 0
             return
@@ -202,7 +190,6 @@ class Engine:
 
     def swap(self):
         (self.theta, self.eta, self.pr), self._alt = self._alt, (self.theta, self.eta, self.pr)
-        self._flat, self._alt_flat = self._alt_flat, self._flat
 
     # ---------------------------------------------------------------- reductions
     def likelihood_device(self):
