@@ -30,8 +30,18 @@ int launch_interleave(const double* src, double* dst, int n_src, int n_dst, int 
 
 int launch_w(const double* own, const double* pw, double* W, int M, int LD, int RNB, int n_runs,
              cudaStream_t st);
+// Where row_n_kernel ALSO writes the new rows, in the run-interleaved layout of a gather table that
+// spans all ranks (a sharded run publishes its new rows this way instead of re-reading them with
+// interleave_runs_kernel): table t serves the runs [gs*group0, gs*(group0+groups)) and holds
+// dst[((run/gs) * n_all + row0 + row) * gs + run%gs][ld].
+struct RowPublish {
+  double* dst[3];
+  int gs[3], group0[3], groups[3];
+  int n_all, row0;
+};
 int launch_n(const double* G, const double* pn, const double* own, const int32_t* deg, double* out,
-             int M, int LD, int RNB, int normalize, int n_runs, cudaStream_t st);
+             int M, int LD, int RNB, int normalize, int n_runs, cudaStream_t st,
+             const RowPublish* publish = nullptr);
 
 int launch_segment_pass_and_fixup(SegArgs a, const double* nbr_pairs, const double* nbr_hexa,
                                   int64_t n_ratings, int n_runs, cudaStream_t st, bool no_long_segments = false);

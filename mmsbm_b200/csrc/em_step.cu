@@ -269,10 +269,20 @@ __global__ void __launch_bounds__(kRowThreads) row_n_kernel(const double* __rest
                                                             const double* __restrict__ own,
                                                             const int32_t* __restrict__ deg,
                                                             double* __restrict__ out, int M, int RNB,
-                                                            int normalize) {
+                                                            int normalize, const RowPublish pub) {
   extern __shared__ __align__(32) unsigned char smem_raw[];
   double* Ps = reinterpret_cast<double*>(smem_raw);          // [RNB][LD]
   const int run = blockIdx.y;
+  // the gather table (if any) that serves this run: the new rows are stored there too
+  double* pdst = nullptr;
+  int pgs = 1, pj = 0;
+  size_t pgrp = 0;
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    if (pub.dst[t] != nullptr && run >= pub.gs[t] * pub.group0[t] && run < pub.gs[t] * (pub.group0[t] + pub.groups[t])) {
+      pdst = pub.dst[t]; pgs = pub.gs[t]; pgrp = (size_t)(run / pub.gs[t]); pj = run % pub.gs[t];
+    }
+  }
   {
     const double2* src = reinterpret_cast<const double2*>(pn + (size_t)run * LD * RNB);
     double2* dst = reinterpret_cast<double2*>(Ps);
@@ -332,6 +342,7 @@ __global__ void __launch_bounds__(kRowThreads) row_n_kernel(const double* __rest
         double4_t v{acc[j][4 * c] * ov.x, acc[j][4 * c + 1] * ov.y, acc[j][4 * c + 2] * ov.z, acc[j][4 * c + 3] * ov.w};
         if (normalize) { v.x = v.x / d; v.y = v.y / d; v.z = v.z / d; v.w = v.w / d; }
         stg256(out_run + (size_t)mr[j] * LD + 4 * c, v);
+        if (pdst) stg256(pdst + (((pgrp * pub.n_all + pub.row0 + mr[j]) * pgs + pj) * LD + 4 * c), v);
       }
     }
   }
@@ -714,8 +725,10 @@ int launch_w(const double* own, const double* pw, double* W, int M, int LD, int 
 }
 
 int launch_n(const double* G, const double* pn, const double* own, const int32_t* deg, double* out,
-             int M, int LD, int RNB, int normalize, int n_runs, cudaStream_t st) {
+             int M, int LD, int RNB, int normalize, int n_runs, cudaStream_t st, const RowPublish* publish) {
   const size_t smem = (size_t)LD * RNB * 8;
+  RowPublish pub{};
+  if (publish) pub = *publish;
   // one row per lane here: two rows cost occupancy (142 registers) and measured slower
   const int rows_env = env_int("MMSBM_ROWS_N", 1);
   // chunks in flight per lane: MMSBM_ROWN_PF (1 = round-1 behaviour); needs (RNB / 4) % PF == 0
@@ -727,7 +740,7 @@ int launch_n(const double* G, const double* pn, const double* own, const int32_t
     const int per = kRowThreads * ((two) ? 2 : 1);                                              \
     const int gx = min((M + per - 1) / per, sm_count() * 2);                                    \
     MMSBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<dim3(gx, n_runs), kRowThreads, smem, st>>>(G, pn, own, deg, out, M, RNB, normalize); \
+    kern<<<dim3(gx, n_runs), kRowThreads, smem, st>>>(G, pn, own, deg, out, M, RNB, normalize, pub); \
     MMSBM_LAUNCH_CHECK("row_n_kernel");                                                         \
     return 0;                                                                                   \
   }
@@ -744,6 +757,7 @@ int launch_n(const double* G, const double* pn, const double* own, const int32_t
   MMSBM_ROW_N(28) MMSBM_ROW_N(32)
 #undef MMSBM_ROW_N_GO
 #undef MMSBM_ROW_N
+  MMSBM_REQUIRE(!publish, MMSBM_ERANGE, "row publishing needs row strides of at most 32 doubles");
   GemmArgs g{G, pn, out, own, deg, M, LD, RNB, RNB, 0, normalize, 0};
   return launch_gemm<true>(g, n_runs, st);
 }

@@ -91,6 +91,21 @@ static GridLayout grid_layout(int U, int I, int K, int L, int S) {
   return g;
 }
 
+// the tables of half `half` of the own buffer as the target of row_n_kernel's second store
+static RowPublish row_publish(const void* base, const GridLayout& g, const Table* tabs, int n_tabs, int half,
+                              int n_all, int row0) {
+  RowPublish p{};
+  for (int k = 0; k < n_tabs && k < 3; ++k) {
+    const Table& t = tabs[k];
+    if (t.groups == 0) continue;
+    p.dst[k] = reinterpret_cast<double*>(const_cast<char*>(static_cast<const char*>(base)) +
+                                         (size_t)half * g.half_bytes + t.off);
+    p.gs[k] = t.gs; p.group0[k] = t.group0; p.groups[k] = t.groups;
+  }
+  p.n_all = n_all; p.row0 = row0;
+  return p;
+}
+
 static const double* table_ptr(const void* base, const GridLayout& g, int half, const Table& t) {
   if (t.groups == 0) return nullptr;
   return reinterpret_cast<const double*>(static_cast<const char*>(base) + (size_t)half * g.half_bytes + t.off);
@@ -151,7 +166,7 @@ static int publish_side(const mmsbm_shard_t& sh, const GridLayout& g, const Tabl
                         const double* own_rows, int n_own, int lo, int half, cudaStream_t st,
                         const Exchange& ex) {
   char* mine = static_cast<char*>(sh.exchange_dev[sh.rank]);
-  for (int k = 0; k < n_tabs; ++k) {
+  for (int k = 0; k < n_tabs && own_rows; ++k) {             // own_rows == NULL: row_n_kernel wrote the slice already
     const Table& t = tabs[k];
     if (t.groups == 0) continue;
     double* dst = reinterpret_cast<double*>(mine + (size_t)half * g.half_bytes + t.off);
@@ -442,6 +457,7 @@ extern "C" int mmsbm_em_run_sharded(const mmsbm_shard_t* shp, int32_t iterations
   const bool dyn = env_int("MMSBM_DYN", n_big >= ((int64_t)1 << 20) ? 1 : 0) != 0;
   const bool alternate = peers && env_int("MMSBM_SHARD_ALTERNATE", 1) != 0;
   const bool overlap = peers && env_int("MMSBM_SHARD_OVERLAP", 1) != 0;   // aux stream beside the main one
+  const bool fuse = env_int("MMSBM_SHARD_FUSE", 1) != 0;   // row_n_kernel writes the table slice itself
   // persistent CTAs of the passes leave a few slots free so that the NCCL kernels of the side stream
   // can start while a pass runs
   if (peers) set_reserved_ctas(env_int("MMSBM_SHARD_RESERVE", 4));
@@ -474,10 +490,13 @@ extern "C" int mmsbm_em_run_sharded(const mmsbm_shard_t* shp, int32_t iterations
       return launch_segment_pass_and_fixup(a, table_ptr(mine, g, cur, g.eta[1]), table_ptr(mine, g, cur, g.eta[0]),
                                            sh.n_ratings_u, S, st);
     };
+    // (row_n_kernel stores the new rows twice: plain into the own buffer and, interleaved, into the own
+    //  slice of the next gather tables -- no separate interleave pass)
     auto finish_users = [&](cudaStream_t fs) -> int {
-      int r = launch_n(wg_u, pn_u, th, sh.udeg_dev, th_n, Uo, d.ldk, d.rnb_u, 1, S, fs);
+      const RowPublish pub = row_publish(mine, g, g.theta, 2, nxt, sh.n_users, sh.user_lo);
+      int r = launch_n(wg_u, pn_u, th, sh.udeg_dev, th_n, Uo, d.ldk, d.rnb_u, 1, S, fs, fuse ? &pub : nullptr);
       if (r) return r;
-      return publish_side(sh, g, g.theta, 2, th_n, Uo, sh.user_lo, nxt, fs, ex);
+      return publish_side(sh, g, g.theta, 2, fuse ? nullptr : th_n, Uo, sh.user_lo, nxt, fs, ex);
     };
     auto pass_items = [&]() -> int {            // gathers theta rows of ALL users, new eta rows of the own items
       if (have_arrival[0]) MMSBM_CUDA(cudaStreamWaitEvent(st, ex.arrived[0][(it + 1) & 1], 0));
@@ -486,9 +505,10 @@ extern "C" int mmsbm_em_run_sharded(const mmsbm_shard_t* shp, int32_t iterations
       return launch_segment_pass_and_fixup(a, table_ptr(mine, g, cur, g.theta[0]), nullptr, sh.n_ratings_i, S, st);
     };
     auto finish_items = [&](cudaStream_t fs) -> int {
-      int r = launch_n(wg_i, pn_i, et, sh.ideg_dev, et_n, Io, d.ldl, d.rnb_i, 1, S, fs);
+      const RowPublish pub = row_publish(mine, g, g.eta, 3, nxt, sh.n_items, sh.item_lo);
+      int r = launch_n(wg_i, pn_i, et, sh.ideg_dev, et_n, Io, d.ldl, d.rnb_i, 1, S, fs, fuse ? &pub : nullptr);
       if (r) return r;
-      return publish_side(sh, g, g.eta, 3, et_n, Io, sh.item_lo, nxt, fs, ex);
+      return publish_side(sh, g, g.eta, 3, fuse ? nullptr : et_n, Io, sh.item_lo, nxt, fs, ex);
     };
     auto reduce_pr = [&](cudaStream_t fs) -> int {   // partial n_pr on fs, its sum over the ranks on the side stream
       int r = launch_pr(emit_items ? et : th, emit_items ? wg_i : wg_u, partial, pr, pr_n, emit_items ? Io : Uo,
@@ -541,8 +561,15 @@ extern "C" int mmsbm_em_run_sharded(const mmsbm_shard_t* shp, int32_t iterations
     if (overlap) MMSBM_CUDA(cudaStreamWaitEvent(st, ex.w2_ready, 0));
     if ((rc = users_first ? pass_items() : pass_users())) return rc;
     MMSBM_MARK(4);
+    if (!emit_after_pass1) {                    // n_pr from pass 2's side: beside its n contraction, on the aux stream
+      if (overlap) {
+        MMSBM_CUDA(cudaEventRecord(ex.pass1_done, st));
+        MMSBM_CUDA(cudaStreamWaitEvent(aux, ex.pass1_done, 0));
+      }
+      if ((rc = reduce_pr(aux))) return rc;
+      if (overlap) MMSBM_CUDA(cudaEventRecord(ex.aux_done, aux));
+    }
     if ((rc = users_first ? finish_items(st) : finish_users(st))) return rc;
-    if (!emit_after_pass1 && (rc = reduce_pr(st))) return rc;   // (exposed: nothing left to hide it behind)
     if ((rc = after_publish(users_first ? 1 : 0))) return rc;
     MMSBM_MARK(5);
     if (overlap) MMSBM_CUDA(cudaStreamWaitEvent(st, ex.aux_done, 0));
