@@ -289,3 +289,16 @@ def test_committed_roofline_fractions_are_physical_and_reproducible():
         assert roof["traffic"] <= rec["dram_bytes_per_iteration"]
         seen += 1
     assert seen >= 3
+
+
+def test_unsupported_shapes_are_refused_before_any_gpu_work(tmp_path, monkeypatch):
+    """The kernels' shape envelope ('Supported shapes') is checked up front with the
+    limit spelled out, instead of failing deep inside the fit."""
+    monkeypatch.chdir(tmp_path)                               # the logger writes mmsbm.log
+    from mmsbm_b200.mmsbm import MMSBM
+    MMSBM(20, 20)._check_shape(5)
+    MMSBM(256, 3)._check_shape(4)                             # wide rows: ratings x groups <= 1024
+    MMSBM(32, 32)._check_shape(31)
+    for K, L, R in ((257, 2, 5), (2, 300, 5), (10, 10, 32), (64, 8, 17), (8, 200, 6)):
+        with pytest.raises(ValueError, match="mmsbm_b200"):
+            MMSBM(K, L)._check_shape(R)
