@@ -302,3 +302,20 @@ def test_unsupported_shapes_are_refused_before_any_gpu_work(tmp_path, monkeypatc
     for K, L, R in ((257, 2, 5), (2, 300, 5), (10, 10, 32), (64, 8, 17), (8, 200, 6)):
         with pytest.raises(ValueError, match="mmsbm_b200"):
             MMSBM(K, L)._check_shape(R)
+
+
+def test_installed_reference_is_the_unmodified_reference():
+    """baseline/_ref (what the CPU arm of bench.py times and tests/test_reference_plugin.py drives) holds
+    the reference's modules byte for byte -- checked wherever both trees exist (the build container)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref, src = os.path.join(root, "baseline", "_ref"), "/root/reference/src"
+    if not (os.path.isdir(ref) and os.path.isdir(src)):
+        pytest.skip("needs both baseline/_ref and /root/reference")
+    names = [f for f in os.listdir(src) if f.endswith(".py") and f != "__init__.py"]
+    assert len(names) == 9
+    for f in names:
+        assert open(os.path.join(ref, f), "rb").read() == open(os.path.join(src, f), "rb").read(), f
+    # and nothing of it is tracked by git
+    import subprocess
+    tracked = subprocess.run(["git", "ls-files", "baseline"], capture_output=True, text=True, cwd=root).stdout.strip()
+    assert tracked == ""
